@@ -1,0 +1,162 @@
+// CABAC kernel: slice data -> syntax (tu_map, TransCoeffLevel, QpY map, SAO parameters).
+//
+// Replaces the reference's serial tile loop + SliceSegmentReader::read_data (src/heic/decoder.rs:114-119,
+// src/hevc/slice.rs:206-231) and its CABAC stack (src/cabac/*).  The arithmetic decoder is inherently
+// serial per substream, so the parallelism is substreams = tiles x WPP rows x images:
+//
+//   TILES == 1   one warp per WPP row of one tile, lane 0 decodes ("warp per substream")
+//   TILES == 32  lane l of warp r decodes row r (+ k*R) of the CTA's l-th tile ("thread per substream");
+//                the 32 context tables of a warp are interleaved so equal context indices share a 32-byte
+//                row of shared memory, and the rows of a tile advance as a wavefront between the warps.
+//
+// R row slots per CTA share the rows of a tile round-robin; with the 2-CTU WPP lag a 16-CTB-wide tile has
+// at most 8 rows in flight, so R = 8 keeps every slot busy.  Rows synchronise through progress counters
+// in shared memory (all rows of a tile live in one CTA, hence on one SM).
+#include <cuda_runtime.h>
+
+#include "cabac_parse.cuh"
+#include "kernels.h"
+
+namespace heic {
+namespace dev {
+
+namespace {
+
+constexpr int kMaxRows = 512;
+
+struct CtaShared {
+  CabacTabs tabs;
+  int progress[kMaxRows];  // CTUs finished per CTB row (TILES == 32: by all lanes of the row's warp)
+  int aborted[32];         // per tile of the CTA
+};
+
+template <int TILES>
+struct SmemSync {
+  volatile int* progress;
+  volatile int* aborted;  // this thread's tile
+  int* status_code;       // global
+  uint8_t* save_base;     // + (row % R) * NUM_CTX_PAD * TILES
+  uint8_t* ctx_base;      // slot tables, used as save areas when every slot owns exactly one row
+  int n_slots, lane, direct;
+
+  __device__ __forceinline__ bool wait(int row, int n) {
+    if (TILES == 1) {
+      while (progress[row] < n && !*aborted) __nanosleep(64);
+    } else {
+      __syncwarp();
+      if (lane == 0)
+        while (progress[row] < n) __nanosleep(64);
+      __syncwarp();
+    }
+    __threadfence_block();
+    return !*aborted;
+  }
+  __device__ __forceinline__ void publish(int row, int n) {
+    __threadfence_block();
+    if (TILES == 1) {
+      progress[row] = n;
+    } else {
+      __syncwarp();
+      if (lane == 0) progress[row] = n;
+    }
+  }
+  __device__ __forceinline__ uint8_t* save_area(int row) {
+    // the snapshot of `row` is consumed by row + 1; with one row per slot it can be written straight into
+    // that row's (still idle) context table
+    if (direct) return ctx_base + (size_t)((row + 1) % n_slots) * NUM_CTX_PAD * TILES;
+    return save_base + (size_t)(row % n_slots) * NUM_CTX_PAD * TILES;
+  }
+  __device__ __forceinline__ void abort(int code) {
+    if (code != -100) atomicCAS(status_code, 0, code);
+    *aborted = 1;
+    __threadfence_block();
+  }
+};
+
+}  // namespace
+
+template <int TILES>
+__global__ void __launch_bounds__(512) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
+                                                    const uint32_t* __restrict__ order, int n_slots) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
+  uint8_t* ctx_all = smem_raw + ((sizeof(CtaShared) + 15) & ~(size_t)15);
+  uint8_t* save_all = ctx_all + (size_t)n_slots * NUM_CTX_PAD * TILES;
+
+  {  // tables -> shared memory
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(gtabs);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh->tabs);
+    for (int i = threadIdx.x; i < (int)(sizeof(CabacTabs) / 4); i += blockDim.x) dst[i] = src[i];
+    for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) sh->progress[i] = 0;
+    if (threadIdx.x < 32) sh->aborted[threadIdx.x] = 0;
+  }
+  __syncthreads();
+
+  const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (TILES == 1 && lane != 0) return;
+  // Idle lanes of a partially filled CTA shadow the geometry of the CTA's first tile but decode nothing.
+  const uint32_t my = order[blockIdx.x * TILES + (TILES == 1 ? 0 : lane)];
+  const bool active = my != 0xffffffffu;
+  const uint32_t tile = active ? my : order[blockIdx.x * TILES];
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+
+  Parser<TILES> P;
+  P.T = &sh->tabs;
+  P.ctx = ctx_all + (size_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0 : lane);
+  P.pp = pp;
+  P.tp = tp;
+  P.tu_map = A.tu_map + tp->tu_off;
+  P.coeff[0] = A.coeff + tp->coeff_off[0];
+  P.coeff[1] = A.coeff + tp->coeff_off[1];
+  P.coeff[2] = A.coeff + tp->coeff_off[2];
+  P.ipm = A.ipm + tp->map4_off;
+  P.ct_depth = A.ct_depth + tp->map8_off;
+  P.qp_map = A.qp_map + tp->map8_off;
+  P.sao = A.sao + tp->sao_off;
+  P.e.data = A.bitstream + tp->bs_off;
+  P.err = active ? 0 : -100;
+
+  SmemSync<TILES> sync;
+  sync.progress = sh->progress;
+  sync.aborted = &sh->aborted[TILES == 1 ? 0 : lane];
+  sync.status_code = &A.status[tile].code;
+  sync.n_slots = n_slots;
+  sync.lane = lane;
+  sync.direct = pp->hctb <= n_slots;
+  sync.ctx_base = ctx_all + (TILES == 1 ? 0 : lane);
+  sync.save_base = save_all + (TILES == 1 ? 0 : lane);
+  if (!active) *sync.aborted = 1;
+
+  const uint32_t ctus = parse_rows<TILES>(P, A.substreams + tp->sub_first, slot, n_slots, sync);
+  if (active) {
+    atomicAdd(&A.status[tile].bins, P.e.bins);
+    atomicAdd(&A.status[tile].ctus, ctus);
+  }
+}
+
+size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
+  return ((sizeof(CtaShared) + 15) & ~(size_t)15) + (size_t)2 * n_slots * NUM_CTX_PAD * tiles_per_cta;
+}
+
+cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,
+                         int tiles_per_cta, int n_slots, cudaStream_t stream) {
+  if (!n_groups) return cudaSuccess;
+  const size_t smem = cabac_smem_bytes(tiles_per_cta, n_slots);
+  const int threads = 32 * n_slots;
+  if (tiles_per_cta == 32) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(cabac_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    cabac_kernel<32><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots);
+  } else {
+    cabac_kernel<1><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace dev
+}  // namespace heic

@@ -1,0 +1,761 @@
+// CABAC engine + slice_segment_data() syntax parser, written as per-thread code: one thread owns one
+// substream (a WPP row of one HEIF grid tile) and carries the arithmetic decoder in registers, with
+// its context table in shared memory.  The kernels in cabac_kernel.cu decide how threads map onto
+// substreams; the same source also compiles for the host so the syntax logic can be unit-tested
+// without a GPU (tests/emul/ — test infrastructure, never linked into the product library).
+//
+// Reference interfaces this replaces:
+//   ArithmeticDecoderEngine::{try_new, decode_decision, decode_bypass, decode_terminate, try_renorm}
+//                                                        src/cabac/arithmetic.rs:23-169
+//   init_all_contexts / init_single_context              src/cabac/arithmetic.rs:40-78
+//   SyntaxElement::init_values_i_slice                   src/cabac/syntax_element.rs:90-242
+//   CabacDecoder binarisations                           src/cabac/decoder.rs:23-284
+//   SliceSegmentReader::read_data / read_coding_tree_unit / sao / coding_quadtree
+//                                                        src/hevc/slice.rs:206-255 (the last two are todo!())
+// Syntax the reference does not implement follows ITU-T H.265 7.3.8 / 9.3 (clauses cited inline).
+#pragma once
+#include "dev_types.h"
+
+namespace heic {
+namespace dev {
+
+// Tables the parser indexes dynamically; copied to shared memory at kernel start.
+struct CabacTabs {
+  // per context state s = pStateIdx<<1|valMps: .x = rangeTabLps[p][0..3] as 4 bytes (Table 9-46),
+  // .y = next state after an MPS | next state after an LPS << 8 (Table 9-45, valMps flip folded in)
+  uint32_t st_lps[128];
+  uint32_t st_next[128];
+  uint8_t diag4[16];      // 6.5.3 up-right diagonal, 4x4: scan pos -> x | y << 2
+  uint8_t diag8[64];      // 8x8: x | y << 3
+  uint8_t diag2[4];       // 2x2: x | y << 1
+  uint8_t inv_diag4[16];  // y << 2 | x -> scan pos
+  uint8_t inv_diag8[64];
+  uint8_t inv_diag2[4];
+  uint8_t sig_map4[16];   // ctxIdxMap of 9.3.4.2.5 for 4x4 blocks
+  uint8_t sig_pat[4][16]; // sigCtx by prevCsbf pattern and yP << 2 | xP (9.3.4.2.5)
+  uint8_t init_value[NUM_CTX_PAD];
+};
+
+#if defined(__CUDA_ARCH__)
+#define HEIC_CLZ(x) __clz(x)
+#else
+#define HEIC_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#endif
+
+HEIC_HD int clip3i(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+HEIC_HD uint32_t compact1by1(uint32_t v) {  // even bits of an 8-bit z-order index -> 4-bit coordinate
+  v &= 0x55u;
+  v = (v | (v >> 1)) & 0x33u;
+  v = (v | (v >> 2)) & 0x0fu;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Arithmetic decoding engine (9.3.4.3).  `val` holds ivlOffset << 22 with up to 22 look-ahead bits of
+// the stream below it, so a renormalisation is two shifts; `look` is the next 16 stream bits, fetched
+// one refill ahead so that the load latency is off the per-bin dependency chain.  Bits past the end
+// of the substream read as zero (same convention as the CPU oracle).
+// ------------------------------------------------------------------------------------------------
+struct Engine {
+  const uint8_t* data;
+  uint32_t pos, end;
+  uint32_t range, val, look;
+  int nbits;
+  uint32_t bins;
+
+  HEIC_HD uint32_t byte_at(uint32_t p) const { return p < end ? data[p] : 0u; }
+  HEIC_HD void fetch() {
+    look = (byte_at(pos) << 8) | byte_at(pos + 1);
+    pos += 2;
+  }
+  // 9.3.2.5 (arithmetic.rs:23-38): ivlCurrRange = 510, ivlOffset = read_bits(9)
+  HEIC_HD void init(const uint8_t* d, uint32_t start, uint32_t stop) {
+    data = d;
+    end = stop;
+    range = 510;
+    val = ((byte_at(start) << 16) | (byte_at(start + 1) << 8) | byte_at(start + 2)) << 7;
+    nbits = 15;
+    pos = start + 3;
+    fetch();
+  }
+  HEIC_HD bool offset_is_illegal() const { return (val >> 22) >= 510u; }
+  HEIC_HD void refill() {
+    if (nbits < 7) {
+      val |= look << (6 - nbits);
+      nbits += 16;
+      fetch();
+    }
+  }
+  // 9.3.4.3.2 (arithmetic.rs:97-135)
+  HEIC_HD int decision(const CabacTabs* T, uint8_t* ctx) {
+    uint32_t s = *ctx;
+    uint32_t lps4 = T->st_lps[s], nx = T->st_next[s];
+    uint32_t q = (range >> 6) & 3u;
+    uint32_t lps = (lps4 >> (q << 3)) & 0xffu;
+    range -= lps;
+    uint32_t scaled = range << 22;
+    int bin = (int)(s & 1u);
+    if (val >= scaled) {
+      val -= scaled;
+      range = lps;
+      bin ^= 1;
+      nx >>= 8;
+    }
+    *ctx = (uint8_t)nx;
+    int sh = HEIC_CLZ(range) - 23;  // arithmetic.rs:137-144, all renorm shifts at once
+    range <<= sh;
+    val <<= sh;
+    nbits -= sh;
+    bins++;
+    refill();
+    return bin;
+  }
+  // 9.3.4.3.4 (arithmetic.rs:146-157)
+  HEIC_HD int bypass() {
+    val <<= 1;
+    nbits--;
+    uint32_t scaled = range << 22;
+    int bin = 0;
+    if (val >= scaled) {
+      val -= scaled;
+      bin = 1;
+    }
+    bins++;
+    refill();
+    return bin;
+  }
+  // 9.3.4.3.5 (arithmetic.rs:159-169)
+  HEIC_HD int terminate() {
+    bins++;
+    range -= 2;
+    if (val >= (range << 22)) return 1;
+    int sh = HEIC_CLZ(range) - 23;
+    range <<= sh;
+    val <<= sh;
+    nbits -= sh;
+    refill();
+    return 0;
+  }
+  HEIC_HD uint32_t fl_bypass(int n) {  // decoder.rs:152-164
+    uint32_t v = 0;
+    for (int i = 0; i < n; i++) v = (v << 1) | (uint32_t)bypass();
+    return v;
+  }
+  HEIC_HD uint32_t tr_bypass(uint32_t cmax) {  // decoder.rs:166-190, cRiceParam 0
+    uint32_t v = 0;
+    while (v < cmax && bypass()) v++;
+    return v;
+  }
+};
+
+// 9.3.2.2 (arithmetic.rs:40-78): initValue -> pStateIdx << 1 | valMps
+HEIC_HD uint8_t context_init_state(int init_value, int slice_qp) {
+  int slope_idx = init_value >> 4, offset_idx = init_value & 15;
+  int m = slope_idx * 5 - 45, n = (offset_idx << 3) - 16;
+  int pre = clip3i(1, 126, ((m * clip3i(0, 51, slice_qp)) >> 4) + n);
+  int mps = pre > 63;
+  int p = mps ? pre - 64 : 63 - pre;
+  return (uint8_t)((p << 1) | mps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Syntax parser.  STRIDE is the distance in bytes between consecutive contexts of this thread's table
+// (1 when a warp serves one substream, 32 when the lanes of a warp serve 32 substreams and their
+// tables are interleaved so that equal context indices fall into one 32-byte row).
+// ------------------------------------------------------------------------------------------------
+template <int STRIDE>
+struct Parser {
+  Engine e;
+  const CabacTabs* T;
+  uint8_t* ctx;
+  const PicParams* pp;
+  const TileParams* tp;
+  uint32_t* tu_map;
+  int16_t* coeff[3];
+  uint8_t *ipm, *ct_depth, *qp_map;
+  uint32_t* sao;
+  // QP state (8.6.1)
+  int is_cu_qp_delta_coded, cu_qp_delta_val, qp_y, last_qp_y, qp_y_pred, first_qg_in_row, qg_x, qg_y;
+  // current CU
+  int part_nxn, chroma_mode, cu_x, cu_y, cu_log2;
+  int pu_mode[4];
+  int err;
+
+  HEIC_HD int dec(int idx) { return e.decision(T, ctx + idx * STRIDE); }
+  HEIC_HD void fail(int code) {
+    if (!err) err = code;
+  }
+
+  HEIC_HD void init_contexts(int slice_qp) {
+    for (int i = 0; i < NUM_CTX; i++) ctx[i * STRIDE] = context_init_state(T->init_value[i], slice_qp);
+  }
+
+  HEIC_HD uint32_t egk_bypass(int k) {  // decoder.rs:206-222 with 32-bit arithmetic
+    int ones = 0;
+    while (e.bypass()) {
+      if (++ones > 31) {
+        fail(-3);
+        return 0;
+      }
+    }
+    uint32_t suffix = e.fl_bypass(ones + k);
+    return (((1u << ones) - 1u) << k) + suffix;
+  }
+  HEIC_HD uint32_t coeff_abs_level_remaining(int rice) {  // decoder.rs:224-261
+    uint32_t prefix = 0;
+    while (prefix < 4 && e.bypass()) prefix++;
+    if (prefix < 4) return (prefix << rice) + e.fl_bypass(rice);
+    return (4u << rice) + egk_bypass(rice + 1);
+  }
+
+  // ---- 7.3.8.3 sao() (todo!() at slice.rs:249-251) -------------------------------------------
+  HEIC_HD void parse_sao(int rx, int ry) {
+    uint32_t* p = sao + (size_t)(ry * pp->wctb + rx) * 4;
+    int merge_left = 0, merge_up = 0;
+    if (rx > 0) merge_left = dec(CTX_SAO_MERGE);
+    if (ry > 0 && !merge_left) merge_up = dec(CTX_SAO_MERGE);
+    if (merge_left || merge_up) {
+      const uint32_t* q = merge_left ? p - 4 : p - (size_t)pp->wctb * 4;
+      p[0] = q[0];
+      p[1] = q[1];
+      p[2] = q[2];
+      p[3] = 0;
+      return;
+    }
+    uint32_t w[3] = {0, 0, 0};
+    int type_c = 0, class_c = 0;
+    int n_comp = pp->chroma ? 3 : 1;
+    for (int c = 0; c < n_comp; c++) {
+      if (!((c == 0 && tp->sao_luma) || (c > 0 && tp->sao_chroma))) continue;
+      int type;
+      if (c == 2) {
+        type = type_c;
+      } else {  // sao_type_idx: TR cMax 2, bin 0 context coded, bin 1 bypass (decoder.rs:93-100)
+        type = 0;
+        if (dec(CTX_SAO_TYPE)) type = e.bypass() ? 2 : 1;
+        if (c == 1) type_c = type;
+      }
+      if (!type) continue;
+      int abs_v[4];
+      for (int i = 0; i < 4; i++) abs_v[i] = (int)e.tr_bypass(7);
+      uint32_t v = (uint32_t)type;
+      if (type == 1) {
+        for (int i = 0; i < 4; i++) {
+          int neg = abs_v[i] ? e.bypass() : 0;
+          int o = neg ? -abs_v[i] : abs_v[i];
+          v |= ((uint32_t)o & 15u) << (8 + 4 * i);
+        }
+        v |= e.fl_bypass(5) << 2;  // sao_band_position
+      } else {
+        int cl;
+        if (c == 0) cl = (int)e.fl_bypass(2);
+        else if (c == 1) cl = class_c = (int)e.fl_bypass(2);
+        else cl = class_c;
+        v |= (uint32_t)cl << 2;
+        v |= ((uint32_t)abs_v[0] & 15u) << 8;
+        v |= ((uint32_t)abs_v[1] & 15u) << 12;
+        v |= ((uint32_t)(-abs_v[2]) & 15u) << 16;
+        v |= ((uint32_t)(-abs_v[3]) & 15u) << 20;
+      }
+      w[c] = v;
+    }
+    p[0] = w[0];
+    p[1] = w[1];
+    p[2] = w[2];
+    p[3] = 0;
+  }
+
+  // ---- scan helpers (6.5.3-6.5.5) ---------------------------------------------------------------
+  // position i of a (1<<lg)x(1<<lg) scan -> x | y << 4
+  HEIC_HD uint32_t scan_xy(int scan_idx, int lg, int i) const {
+    if (lg == 0) return 0;
+    if (scan_idx == 0) {
+      uint32_t v;
+      if (lg == 2) {
+        v = T->diag4[i];
+        return (v & 3u) | ((v >> 2) << 4);
+      }
+      if (lg == 3) {
+        v = T->diag8[i];
+        return (v & 7u) | ((v >> 3) << 4);
+      }
+      v = T->diag2[i];
+      return (v & 1u) | ((v >> 1) << 4);
+    }
+    uint32_t a = (uint32_t)i & ((1u << lg) - 1u), b = (uint32_t)i >> lg;
+    return scan_idx == 1 ? (a | (b << 4)) : (b | (a << 4));
+  }
+  HEIC_HD int scan_inv(int scan_idx, int lg, int x, int y) const {
+    if (lg == 0) return 0;
+    if (scan_idx == 0) {
+      if (lg == 2) return T->inv_diag4[(y << 2) | x];
+      if (lg == 3) return T->inv_diag8[(y << 3) | x];
+      return T->inv_diag2[(y << 1) | x];
+    }
+    return scan_idx == 1 ? ((y << lg) | x) : ((x << lg) | y);
+  }
+
+  HEIC_HD int last_sig_coeff_prefix(int ctx_base, int c_idx, int log2) {  // decoder.rs:109-130
+    int ctx_offset, ctx_shift;
+    if (c_idx == 0) {
+      ctx_offset = 3 * (log2 - 2) + ((log2 - 1) >> 2);
+      ctx_shift = (log2 + 1) >> 2;
+    } else {
+      ctx_offset = 15;
+      ctx_shift = log2 - 2;
+    }
+    int c_max = (log2 << 1) - 1, v = 0;
+    while (v < c_max && dec(ctx_base + (v >> ctx_shift) + ctx_offset)) v++;
+    return v;
+  }
+
+  // ---- 7.3.8.11 residual_coding + 9.3.4.2.4-7; writes TransCoeffLevel (raster n x n) to out -------
+  HEIC_HD int residual_coding(int log2, int c_idx, int pred_mode, int16_t* out) {
+    const int n = 1 << log2;
+    int tskip = 0;
+    if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
+    int last_x = last_sig_coeff_prefix(CTX_LAST_X, c_idx, log2);
+    int last_y = last_sig_coeff_prefix(CTX_LAST_Y, c_idx, log2);
+    if (last_x > 3) {
+      int nb = (last_x >> 1) - 1;
+      last_x = (1 << nb) * (2 + (last_x & 1)) + (int)e.fl_bypass(nb);
+    }
+    if (last_y > 3) {
+      int nb = (last_y >> 1) - 1;
+      last_y = (1 << nb) * (2 + (last_y & 1)) + (int)e.fl_bypass(nb);
+    }
+    int scan_idx = 0;
+    if (log2 == 2 || (log2 == 3 && c_idx == 0)) {
+      if (pred_mode >= 6 && pred_mode <= 14) scan_idx = 2;
+      else if (pred_mode >= 22 && pred_mode <= 30) scan_idx = 1;
+    }
+    if (scan_idx == 2) {
+      int t = last_x;
+      last_x = last_y;
+      last_y = t;
+    }
+    const int lg_sb = log2 - 2;
+    const int last_sub_block = scan_inv(scan_idx, lg_sb, last_x >> 2, last_y >> 2);
+    const int last_scan_pos = scan_inv(scan_idx, 2, last_x & 3, last_y & 3);
+    const int sb_w = 1 << lg_sb;
+    const int sig_base = CTX_SIG + (c_idx ? 27 : 0);
+    // sigCtx offset for the non-4x4, non-DC case (9.3.4.2.5)
+    const int sig_off = c_idx == 0 ? ((log2 == 3) ? (scan_idx == 0 ? 9 : 15) : 21) : ((log2 == 3) ? 9 : 12);
+    uint64_t csbf = 0;  // bit ys*8+xs
+    int greater1_ctx = 1, first_sub_block = 1;
+    for (int i = last_sub_block; i >= 0 && !err; i--) {
+      uint32_t sxy = scan_xy(scan_idx, lg_sb, i);
+      const int xs = (int)(sxy & 15u), ys = (int)(sxy >> 4);
+      int right = (xs < sb_w - 1) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1u) : 0;
+      int below = (ys < sb_w - 1) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1u) : 0;
+      int infer_sb_dc = 0, coded = 1;
+      if (i < last_sub_block && i > 0) {
+        coded = dec(CTX_CSBF + (c_idx ? 2 : 0) + (right | below));
+        infer_sb_dc = 1;
+      }
+      if (coded) csbf |= (uint64_t)1 << (ys * 8 + xs);
+      uint32_t sig = 0;
+      int n_start = 15;
+      if (i == last_sub_block) {
+        n_start = last_scan_pos - 1;
+        sig = 1u << last_scan_pos;
+      }
+      if (coded) {
+        const int prev_csbf = right | (below << 1);
+        const int sb_off = (c_idx == 0 && (xs | ys)) ? 3 : 0;
+        for (int k = n_start; k >= 0; k--) {
+          if (k > 0 || !infer_sb_dc) {
+            uint32_t pxy = scan_xy(scan_idx, 2, k);
+            int xp = (int)(pxy & 15u), yp = (int)(pxy >> 4);
+            int sig_ctx;
+            if (log2 == 2) sig_ctx = T->sig_map4[(yp << 2) + xp];
+            else if ((xs | ys | xp | yp) == 0) sig_ctx = 0;
+            else sig_ctx = T->sig_pat[prev_csbf][(yp << 2) | xp] + sb_off + sig_off;
+            if (dec(sig_base + sig_ctx)) {
+              sig |= 1u << k;
+              infer_sb_dc = 0;
+            }
+          } else {
+            sig |= 1u;  // inferred DC of a coded sub-block with no other significant coefficient
+          }
+        }
+      }
+      if (!sig) continue;
+      // 9.3.4.2.6 / 9.3.4.2.7: up to 8 greater1 flags, one greater2 flag
+      int ctx_set = (i > 0 && c_idx == 0) ? 2 : 0;
+      if (!first_sub_block && greater1_ctx == 0) ctx_set++;
+      first_sub_block = 0;
+      greater1_ctx = 1;
+      uint32_t g1 = 0;
+      int num_g1 = 0, last_g1_pos = -1;
+      const int last_sig = 31 - HEIC_CLZ(sig);
+      const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
+      {
+        uint32_t m = sig;
+        while (m && num_g1 < 8) {
+          int k = 31 - HEIC_CLZ(m);
+          m &= ~(1u << k);
+          int f = dec(CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2) + greater1_ctx);
+          num_g1++;
+          if (f) {
+            g1 |= 1u << k;
+            greater1_ctx = 0;
+            if (last_g1_pos < 0) last_g1_pos = k;
+          } else if (greater1_ctx > 0 && greater1_ctx < 3) {
+            greater1_ctx++;
+          }
+        }
+      }
+      const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
+      int g2 = 0;
+      if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
+      uint32_t sign = 0;
+      {
+        uint32_t m = sig;
+        if (sign_hidden) m &= ~(1u << first_sig);
+        while (m) {
+          int k = 31 - HEIC_CLZ(m);
+          m &= ~(1u << k);
+          if (e.bypass()) sign |= 1u << k;
+        }
+      }
+      int num_sig = 0, sum_abs = 0, rice = 0;
+      uint32_t m = sig;
+      while (m) {
+        int k = 31 - HEIC_CLZ(m);
+        m &= ~(1u << k);
+        int base = 1 + (int)((g1 >> k) & 1u) + ((k == last_g1_pos) ? g2 : 0);
+        int abs_level = base;
+        if (base == ((num_sig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
+          uint32_t rem = coeff_abs_level_remaining(rice);
+          if (rem > 32768u) {
+            fail(-3);
+            return tskip;
+          }
+          abs_level = base + (int)rem;
+          if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
+        }
+        int v = ((sign >> k) & 1u) ? -abs_level : abs_level;
+        if (sign_hidden) {
+          sum_abs += abs_level;
+          if (k == first_sig && (sum_abs & 1)) v = -v;
+        }
+        uint32_t pxy = scan_xy(scan_idx, 2, k);
+        int xc = (xs << 2) + (int)(pxy & 15u), yc = (ys << 2) + (int)(pxy >> 4);
+        out[yc * n + xc] = (int16_t)clip3i(-32768, 32767, v);
+        num_sig++;
+      }
+    }
+    return tskip;
+  }
+
+  // ---- 8.6.1 ------------------------------------------------------------------------------------
+  HEIC_HD void set_qp_pred(int x_qg, int y_qg) {
+    int qp_prev = first_qg_in_row ? tp->slice_qp : last_qp_y;
+    first_qg_in_row = 0;
+    int ctb_mask = (1 << pp->log2_ctb) - 1;
+    int qa = qp_prev, qb = qp_prev;
+    if (x_qg & ctb_mask) qa = qp_map[(y_qg >> 3) * pp->w8 + ((x_qg - 1) >> 3)];
+    if (y_qg & ctb_mask) qb = qp_map[((y_qg - 1) >> 3) * pp->w8 + (x_qg >> 3)];
+    qp_y_pred = (qa + qb + 1) >> 1;
+    qp_y = qp_y_pred;
+  }
+
+  // ---- 7.3.8.10 transform_unit ------------------------------------------------------------------
+  // z4: z-order index of the TU's 4x4 origin inside its CTB; ctb_addr: raster CTB address
+  HEIC_HD void transform_unit(int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr,
+                              uint32_t ctb_addr, uint32_t z4) {
+    const int pb_shift = part_nxn ? cu_log2 - 1 : cu_log2;
+    const int luma_mode = pu_mode[(((x0 - cu_x) >> pb_shift) & 1) | ((((y0 - cu_y) >> pb_shift) & 1) << 1)];
+    const int has_chroma = pp->chroma && (log2 > 2 || blk_idx == 3);
+    const int log2c = log2 > 2 ? log2 - 1 : 2;
+    const int any_cbf = cbf_luma | cbf_cb | cbf_cr;  // 7.3.8.10: parent-inherited chroma cbfs count for blkIdx 0..2 too
+    if (!has_chroma) cbf_cb = cbf_cr = 0;
+    if (any_cbf && pp->cu_qp_delta_enabled && !is_cu_qp_delta_coded) {
+      // cu_qp_delta_abs: prefix TR cMax 5 (bin 0 ctx 0, bins 1-4 ctx 1) + EG0 suffix (decoder.rs:263-284)
+      int v = 0;
+      while (v < 5 && dec(CTX_CU_QP_DELTA + (v ? 1 : 0))) v++;
+      if (v == 5) v += (int)egk_bypass(0);
+      int neg = v ? e.bypass() : 0;
+      is_cu_qp_delta_coded = 1;
+      cu_qp_delta_val = neg ? -v : v;
+      if (cu_qp_delta_val < -26 || cu_qp_delta_val > 25) fail(-3);
+      qp_y = (qp_y_pred + cu_qp_delta_val + 52) % 52;
+    }
+    if (err) return;
+    const int ctb4 = 1 << (pp->log2_ctb - 2);
+    const uint32_t ti = ctb_addr * (uint32_t)(ctb4 * ctb4) + z4;
+    int ts0 = 0, ts1 = 0, ts2 = 0;
+    if (cbf_luma) ts0 = residual_coding(log2, 0, luma_mode, coeff[0] + (size_t)ti * 16);
+    if (cbf_cb | cbf_cr) {
+      const size_t off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
+      if (cbf_cb) ts1 = residual_coding(log2c, 1, chroma_mode, coeff[1] + off_c);
+      if (cbf_cr) ts2 = residual_coding(log2c, 2, chroma_mode, coeff[2] + off_c);
+    }
+    tu_map[ti] = 1u | ((uint32_t)(log2 - 2) << 1) | ((uint32_t)cbf_luma << 3) | ((uint32_t)cbf_cb << 4) |
+                 ((uint32_t)cbf_cr << 5) | ((uint32_t)has_chroma << 6) | ((uint32_t)luma_mode << 7) |
+                 ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |
+                 ((uint32_t)ts1 << 26) | ((uint32_t)ts2 << 27);
+  }
+
+  // ---- 7.3.8.8 transform_tree, walked iteratively in z-order over the CU's 4x4 blocks -----------
+  HEIC_HD void transform_tree(uint32_t ctb_addr, uint32_t z4_cu) {
+    const int intra_split = part_nxn;
+    const int max_depth = pp->max_trafo_depth_intra + intra_split;
+    const uint32_t n4 = 1u << (2 * (cu_log2 - 2));
+    uint32_t cb_mask = 0, cr_mask = 0;  // bit d: cbf_cb / cbf_cr of the current node at trafoDepth d
+    uint32_t z = 0;
+    while (z < n4 && !err) {
+      int lvl = cu_log2 - 2;  // largest block whose origin is z
+      if (z) {
+        int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
+        if (tz < lvl) lvl = tz;
+      }
+      int log2 = lvl + 2;
+      for (;;) {
+        const int depth = cu_log2 - log2;
+        int split;
+        if (log2 <= pp->log2_max_tb && log2 > pp->log2_min_tb && depth < max_depth && !(intra_split && depth == 0))
+          split = dec(CTX_SPLIT_TRANSFORM + 5 - log2);
+        else
+          split = (log2 > pp->log2_max_tb) || (intra_split && depth == 0);
+        int cbf_cb = 0, cbf_cr = 0;
+        if (pp->chroma) {
+          int par_cb = depth ? (int)((cb_mask >> (depth - 1)) & 1u) : 1;
+          int par_cr = depth ? (int)((cr_mask >> (depth - 1)) & 1u) : 1;
+          if (log2 > 2) {
+            if (par_cb) cbf_cb = dec(CTX_CBF_CHROMA + depth);
+            if (par_cr) cbf_cr = dec(CTX_CBF_CHROMA + depth);
+          } else {  // inferred from the parent when log2TrafoSize == 2
+            cbf_cb = depth ? par_cb : 0;
+            cbf_cr = depth ? par_cr : 0;
+          }
+        }
+        cb_mask = (cb_mask & ~(1u << depth)) | ((uint32_t)cbf_cb << depth);
+        cr_mask = (cr_mask & ~(1u << depth)) | ((uint32_t)cbf_cr << depth);
+        if (!split) {
+          int cbf_luma = dec(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));  // always present for intra CUs
+          int x0 = cu_x + (int)(compact1by1(z) << 2), y0 = cu_y + (int)(compact1by1(z >> 1) << 2);
+          transform_unit(x0, y0, log2, (int)(z & 3u), cbf_luma, cbf_cb, cbf_cr, ctb_addr, z4_cu + z);
+          break;
+        }
+        log2--;
+      }
+      z += 1u << (2 * (log2 - 2));
+    }
+  }
+
+  // ---- 8.4.2 ------------------------------------------------------------------------------------
+  HEIC_HD int derive_luma_mode(int x, int y, int prev_flag, int mpm_idx, int rem) {
+    int cand_a = 1, cand_b = 1;
+    if (x > 0) cand_a = ipm[(y >> 2) * pp->w4 + ((x - 1) >> 2)];
+    if (y > 0 && ((y - 1) >> pp->log2_ctb) == (y >> pp->log2_ctb)) cand_b = ipm[((y - 1) >> 2) * pp->w4 + (x >> 2)];
+    int c0, c1, c2;
+    if (cand_a == cand_b) {
+      if (cand_a < 2) {
+        c0 = 0;
+        c1 = 1;
+        c2 = 26;
+      } else {
+        c0 = cand_a;
+        c1 = 2 + ((cand_a + 29) & 31);
+        c2 = 2 + ((cand_a - 2 + 1) & 31);
+      }
+    } else {
+      c0 = cand_a;
+      c1 = cand_b;
+      if (cand_a != 0 && cand_b != 0) c2 = 0;
+      else if (cand_a != 1 && cand_b != 1) c2 = 1;
+      else c2 = 26;
+    }
+    if (prev_flag) return mpm_idx == 0 ? c0 : (mpm_idx == 1 ? c1 : c2);
+    int t;
+    if (c0 > c1) t = c0, c0 = c1, c1 = t;
+    if (c0 > c2) t = c0, c0 = c2, c2 = t;
+    if (c1 > c2) t = c1, c1 = c2, c2 = t;
+    int mode = rem;
+    if (mode >= c0) mode++;
+    if (mode >= c1) mode++;
+    if (mode >= c2) mode++;
+    return mode;
+  }
+
+  // ---- 7.3.8.5 coding_unit (I slice) -------------------------------------------------------------
+  HEIC_HD void coding_unit(int x0, int y0, int log2, uint32_t ctb_addr, uint32_t z4_cu) {
+    const int n = 1 << log2;
+    cu_x = x0;
+    cu_y = y0;
+    cu_log2 = log2;
+    part_nxn = 0;
+    if (pp->cu_qp_delta_enabled) {
+      int mask = (1 << pp->log2_min_cu_qp_delta_size) - 1;
+      int x_qg = x0 & ~mask, y_qg = y0 & ~mask;
+      if (x_qg != qg_x || y_qg != qg_y) {
+        qg_x = x_qg;
+        qg_y = y_qg;
+        set_qp_pred(x_qg, y_qg);
+      }
+      qp_y = (qp_y_pred + cu_qp_delta_val + 52) % 52;
+    }
+    if (log2 == pp->log2_min_cb) part_nxn = !dec(CTX_PART_MODE);  // decoder.rs:136-149
+    if (part_nxn && log2 == 3 && pp->log2_min_tb >= 3) {
+      fail(-3);
+      return;
+    }
+    const int n_pu = part_nxn ? 4 : 1, pb = part_nxn ? n >> 1 : n;
+    int prev[4];
+    for (int k = 0; k < n_pu; k++) prev[k] = dec(CTX_PREV_INTRA);
+    for (int k = 0; k < n_pu; k++) {
+      int mpm_idx = 0, rem = 0;
+      if (prev[k]) mpm_idx = (int)e.tr_bypass(2);
+      else rem = (int)e.fl_bypass(5);
+      int px = x0 + (k & 1) * pb, py = y0 + (k >> 1) * pb;
+      int mode = derive_luma_mode(px, py, prev[k], mpm_idx, rem);
+      pu_mode[k] = mode;
+      // neighbours only ever read the right column and the bottom row of a prediction block
+      const int b4 = pb >> 2, x4 = px >> 2, y4 = py >> 2;
+      for (int j = 0; j < b4; j++) ipm[(y4 + j) * pp->w4 + x4 + b4 - 1] = (uint8_t)mode;
+      for (int j = 0; j < b4 - 1; j++) ipm[(y4 + b4 - 1) * pp->w4 + x4 + j] = (uint8_t)mode;
+    }
+    if (!part_nxn) pu_mode[1] = pu_mode[2] = pu_mode[3] = pu_mode[0];
+    chroma_mode = 0;
+    if (pp->chroma) {  // intra_chroma_pred_mode (decoder.rs:23-35,192-204) + 8.4.3
+      int idx = 4;
+      if (dec(CTX_CHROMA_PRED)) idx = (int)e.fl_bypass(2);
+      const int luma = pu_mode[0];
+      if (idx == 4) {
+        chroma_mode = luma;
+      } else {
+        int m = idx == 0 ? 0 : (idx == 1 ? 26 : (idx == 2 ? 10 : 1));
+        chroma_mode = (m == luma) ? 34 : m;
+      }
+    }
+    transform_tree(ctb_addr, z4_cu);
+    // QpY of the CU (8.6.1): CuQpDeltaVal decoded anywhere inside the CU applies to all of it
+    for (int yy = y0 >> 3; yy < (y0 + n) >> 3; yy++)
+      for (int xx = x0 >> 3; xx < (x0 + n) >> 3; xx++) qp_map[yy * pp->w8 + xx] = (uint8_t)qp_y;
+    last_qp_y = qp_y;
+  }
+
+  // ---- 7.3.8.4 coding_quadtree (todo!() at slice.rs:253-255), iterative z-order walk of one CTB ---
+  HEIC_HD void coding_tree_unit(int rx, int ry) {
+    const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
+    const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
+    const int x_ctb = rx << log2_ctb, y_ctb = ry << log2_ctb;
+    if (!pp->cu_qp_delta_enabled) qp_y = tp->slice_qp;
+    if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
+    const int max_lvl = log2_ctb - log2_min_cb;
+    const uint32_t n_min = 1u << (2 * max_lvl);
+    uint32_t z = 0;
+    while (z < n_min && !err) {
+      int lvl = max_lvl;
+      if (z) {
+        int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
+        if (tz < lvl) lvl = tz;
+      }
+      int log2 = log2_min_cb + lvl;
+      const int x0 = x_ctb + (int)(compact1by1(z) << log2_min_cb), y0 = y_ctb + (int)(compact1by1(z >> 1) << log2_min_cb);
+      if (x0 >= pp->w || y0 >= pp->h) {  // quadrant entirely outside the picture: not coded
+        z += 1u << (2 * lvl);
+        continue;
+      }
+      for (;;) {
+        const int depth = log2_ctb - log2, n = 1 << log2;
+        int split;
+        if (x0 + n <= pp->w && y0 + n <= pp->h && log2 > log2_min_cb) {
+          int inc = 0;
+          if (x0 > 0 && ct_depth[(y0 >> 3) * pp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
+          if (y0 > 0 && ct_depth[((y0 - 1) >> 3) * pp->w8 + (x0 >> 3)] > depth) inc++;
+          split = dec(CTX_SPLIT_CU + inc);
+        } else {
+          split = log2 > log2_min_cb;
+        }
+        if (pp->cu_qp_delta_enabled && log2 >= pp->log2_min_cu_qp_delta_size) {
+          is_cu_qp_delta_coded = 0;
+          cu_qp_delta_val = 0;
+        }
+        if (!split) break;
+        log2--;
+      }
+      {
+        const int depth = log2_ctb - log2, b8 = 1 << (log2 - 3), x8 = x0 >> 3, y8 = y0 >> 3;
+        for (int j = 0; j < b8; j++) ct_depth[(y8 + j) * pp->w8 + x8 + b8 - 1] = (uint8_t)depth;
+        for (int j = 0; j < b8 - 1; j++) ct_depth[(y8 + b8 - 1) * pp->w8 + x8 + j] = (uint8_t)depth;
+      }
+      coding_unit(x0, y0, log2, ctb_addr, z << (2 * (log2_min_cb - 2)));
+      z += 1u << (2 * (log2 - log2_min_cb));
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// 7.3.8.1 slice_segment_data(): the CTU loop of slice.rs:206-231 with the WPP handling the reference
+// lacks: every CTB row is its own substream located by its entry point, the engine is
+// re-initialised there (9.3.2.5) and the contexts are synchronised from the row above after its
+// second CTU (9.3.2.2 / 9.3.2.4).  `slot` of `n_slots` threads share the rows of one picture
+// round-robin; Sync provides the wavefront:
+//   bool wait(int row, int n_ctus)      block until `row` has finished n_ctus CTUs (false: tile aborted)
+//   void publish(int row, int n_ctus)   announce progress of `row`
+//   uint8_t* save_area(int row)         context snapshot of `row` (same STRIDE interleave as ctx)
+//   void abort(int code)                record the failure; every later wait() on this tile returns false
+// Returns the number of CTUs decoded by this thread.
+// ------------------------------------------------------------------------------------------------
+template <int STRIDE, class Sync>
+HEIC_HD uint32_t parse_rows(Parser<STRIDE>& P, const uint32_t* substreams, int slot, int n_slots, Sync& sync) {
+  const PicParams* pp = P.pp;
+  const TileParams* tp = P.tp;
+  const int wpp = pp->wpp, wctb = pp->wctb, hctb = pp->hctb;
+  const int n_ctb = wctb * hctb;
+  uint32_t ctus = 0;
+  P.qp_y = P.last_qp_y = tp->slice_qp;
+  P.qp_y_pred = tp->slice_qp;
+  P.qg_x = P.qg_y = -1;
+  P.is_cu_qp_delta_coded = 0;
+  P.cu_qp_delta_val = 0;
+  P.first_qg_in_row = 1;
+  P.e.bins = 0;
+  // Every thread walks all of its (row, CTU) steps even after a failure, so that the wavefront
+  // hand-shakes stay matched and no dependent row can hang; a failed thread just stops parsing.
+  for (int ry = slot; ry < hctb; ry += n_slots) {
+    for (int rx = 0; rx < wctb; rx++) {
+      if (wpp && ry > 0) {
+        int need = rx == 0 ? (wctb < 2 ? wctb : 2) : rx + 1;
+        if (!sync.wait(ry - 1, need)) P.fail(-100);  // another row of this tile failed and recorded its code
+      }
+      if (!P.err) {
+        if (rx == 0 && (ry == 0 || wpp)) {
+          uint32_t start = tp->data_off + (wpp ? substreams[ry] : 0u);
+          uint32_t stop = (wpp && ry + 1 < (int)tp->n_sub) ? tp->data_off + substreams[ry + 1] : tp->bs_len;
+          P.e.init(P.e.data, start, stop);
+          if (P.e.offset_is_illegal()) P.fail(-3);  // arithmetic.rs:33-36
+          if (ry == 0 || wctb == 1) {
+            P.init_contexts(tp->slice_qp);
+          } else {
+            const uint8_t* src = sync.save_area(ry - 1);
+            if (src != P.ctx)
+              for (int i = 0; i < NUM_CTX; i++) P.ctx[i * STRIDE] = src[i * STRIDE];
+          }
+          P.first_qg_in_row = 1;
+        }
+        if (!P.err) P.coding_tree_unit(rx, ry);
+        if (!P.err) {
+          ctus++;
+          if (wpp && rx == 1 && ry + 1 < hctb) {
+            uint8_t* dst = sync.save_area(ry);
+            for (int i = 0; i < NUM_CTX; i++) dst[i * STRIDE] = P.ctx[i * STRIDE];
+          }
+          const int addr = ry * wctb + rx;
+          const int end_of_slice = P.e.terminate();  // end_of_slice_segment_flag (slice.rs:214)
+          if (end_of_slice != (addr == n_ctb - 1)) P.fail(-3);
+          else if (wpp && rx == wctb - 1 && !end_of_slice && !P.e.terminate()) P.fail(-3);  // end_of_subset_one_bit (slice.rs:222-227)
+        }
+        if (P.err) sync.abort(P.err);
+      }
+      sync.publish(ry, rx + 1);
+    }
+  }
+  return ctus;
+}
+
+}  // namespace dev
+}  // namespace heic

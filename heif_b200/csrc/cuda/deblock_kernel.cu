@@ -1,0 +1,255 @@
+// Stage 4: deblocking filter (H.265 8.7.2), in place on the reconstruction arena.  Absent from the
+// reference.  All-intra pictures: bS = 2 on every transform-block edge of the 8x8 grid (CU and PU edges
+// are transform-block edges too), picture borders are not filtered, and HEIF grid tiles are separate
+// pictures, so nothing crosses a tile.
+//
+// Edge-parallel formulation: the vertical-edge pass only touches columns [8k-4, 8k+4) around edge 8k and
+// the horizontal-edge pass only rows [8j-4, 8j+4), so the "shifted" 8x8 cell [8k-4,8k+4) x [8j-4,8j+4) is
+// closed under both passes: one thread loads it into registers, filters its vertical edge, then its
+// horizontal edge on the result (the order 8.7.2 prescribes), and writes it back — one read and one write
+// of every sample, no halo, no second pass over HBM.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace heic {
+namespace dev {
+
+namespace {
+
+__device__ const uint8_t kBetaTable[52] = {0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  0,  6,  7,
+                                           8,  9,  10, 11, 12, 13, 14, 15, 16, 17, 18, 20, 22, 24, 26, 28, 30, 32,
+                                           34, 36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64};
+__device__ const uint8_t kTcTable[54] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,  0,  0,  0,  0,  0,  0,  0,
+                                         1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2,  2,  2,  3,  3,  3,  3,  4,
+                                         4, 4, 5, 5, 6, 6, 7, 8, 9, 10, 11, 13, 14, 16, 18, 20, 22, 24};
+__device__ const uint8_t kChromaQp[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37};
+
+__device__ __forceinline__ int clip3(int lo, int hi, int v) { return min(hi, max(lo, v)); }
+__device__ __forceinline__ int clip8(int v) { return min(255, max(0, v)); }
+
+__device__ __forceinline__ uint32_t interleave4(uint32_t v) {  // 4-bit coordinate -> even bits
+  v &= 0x0fu;
+  v = (v | (v << 2)) & 0x33u;
+  v = (v | (v << 1)) & 0x55u;
+  return v;
+}
+
+struct Pic {
+  const uint32_t* tu_map;
+  const uint8_t* qp_map;
+  int w8, log2_ctb, wctb;
+};
+
+// log2 size of the transform unit covering luma sample (x, y): probe the aligned candidate origins.
+__device__ __forceinline__ int tu_log2_at(const Pic& p, int x, int y) {
+  const int ctb4 = 1 << (p.log2_ctb - 2);
+  const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
+  const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
+  const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const uint32_t w = tu[z & ~((1u << (2 * l)) - 1u)];
+    if ((w & TU_ORIGIN) && (int)((w >> 1) & 3u) == l) return l + 2;
+  }
+  return 5;  // not reached for a fully parsed picture
+}
+__device__ __forceinline__ int qp_at(const Pic& p, int x, int y) { return p.qp_map[(y >> 3) * p.w8 + (x >> 3)]; }
+
+// Luma edge filter over one 4-line segment held in registers: P(i, l) / Q(i, l) are references.
+// s[l][0..7] = p3 p2 p1 p0 q0 q1 q2 q3 of line l.
+__device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_p, int qp_q, int beta_off2, int tc_off2) {
+  const int qpl = (qp_p + qp_q + 1) >> 1;
+  const int beta = kBetaTable[clip3(0, 51, qpl + beta_off2)];
+  const int tc = kTcTable[clip3(0, 53, qpl + 2 + tc_off2)];
+  const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
+  const int dq0 = abs(s[0][6] - 2 * s[0][5] + s[0][4]), dq3 = abs(s[3][6] - 2 * s[3][5] + s[3][4]);
+  const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
+  if (dpq0 + dpq3 >= beta) return;
+  const bool s0 = 2 * dpq0 < (beta >> 2) && abs(s[0][0] - s[0][3]) + abs(s[0][4] - s[0][7]) < (beta >> 3) &&
+                  abs(s[0][3] - s[0][4]) < ((5 * tc + 1) >> 1);
+  const bool s3 = 2 * dpq3 < (beta >> 2) && abs(s[3][0] - s[3][3]) + abs(s[3][4] - s[3][7]) < (beta >> 3) &&
+                  abs(s[3][3] - s[3][4]) < ((5 * tc + 1) >> 1);
+  const bool strong = s0 && s3;
+  const bool dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const int p3 = s[l][0], p2 = s[l][1], p1 = s[l][2], p0 = s[l][3];
+    const int q0 = s[l][4], q1 = s[l][5], q2 = s[l][6], q3 = s[l][7];
+    if (strong) {
+      s[l][3] = clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      s[l][2] = clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+      s[l][1] = clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+      s[l][4] = clip3(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      s[l][5] = clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+      s[l][6] = clip3(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+    } else {
+      int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+      if (abs(delta) < tc * 10) {
+        delta = clip3(-tc, tc, delta);
+        s[l][3] = clip8(p0 + delta);
+        s[l][4] = clip8(q0 - delta);
+        if (dep) s[l][2] = clip8(p1 + clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
+        if (deq) s[l][5] = clip8(q1 + clip3(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void filter_chroma_segment(int (&s)[4][8], int qp_p, int qp_q, int c_qp_off, int tc_off2) {
+  const int qpi = ((qp_p + qp_q + 1) >> 1) + c_qp_off;  // cQpPicOffset: PPS offset only (8.7.2.5.5)
+  const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
+  const int tc = kTcTable[clip3(0, 53, qpc + 2 + tc_off2)];
+  if (!tc) return;
+#pragma unroll
+  for (int l = 0; l < 4; l++) {
+    const int p1 = s[l][2], p0 = s[l][3], q0 = s[l][4], q1 = s[l][5];
+    const int delta = clip3(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
+    s[l][3] = clip8(p0 + delta);
+    s[l][4] = clip8(q0 - delta);
+  }
+}
+
+// One shifted cell of plane CIDX.  (k, j): cell indices; the cell covers plane samples
+// [8k-4, 8k+4) x [8j-4, 8j+4) clipped to the picture.
+template <int CIDX>
+__device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int pitch, int pw, int ph, int k, int j,
+                                             int beta_off2, int tc_off2, int c_qp_off) {
+  constexpr int SUB = CIDX ? 1 : 0;
+  const int x0 = 8 * k - 4, y0 = 8 * j - 4;
+  const bool has_left = k > 0, has_right = 8 * k < pw, has_top = j > 0, has_bottom = 8 * j < ph;
+  int px[8][8];
+  // rows y0 .. y0+7; the left half [x0, x0+4) exists when k > 0, the right half when 8k < pw
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const bool row_ok = r < 4 ? has_top : has_bottom;
+    uint32_t a = 0, b = 0;
+    if (row_ok) {
+      const uint8_t* row = plane + (size_t)(y0 + r) * pitch;
+      if (has_left) a = *reinterpret_cast<const uint32_t*>(row + x0);
+      if (has_right) b = *reinterpret_cast<const uint32_t*>(row + x0 + 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      px[r][i] = (int)((a >> (8 * i)) & 0xffu);
+      px[r][4 + i] = (int)((b >> (8 * i)) & 0xffu);
+    }
+  }
+  bool changed = false;
+  // ---- vertical edge at x = 8k (luma: every 8 samples; chroma 4:2:0: every 8 chroma = 16 luma samples) ----
+  if (has_left && has_right) {
+    const int xl = (8 * k) << SUB;  // luma position of the edge
+#pragma unroll
+    for (int seg = 0; seg < 2; seg++) {
+      if (seg == 0 ? !has_top : !has_bottom) continue;
+      const int yl = (y0 + 4 * seg) << SUB;
+      const int lg = tu_log2_at(pic, xl, yl);
+      if (xl & ((1 << lg) - 1)) continue;  // not a transform-block edge
+      const int qp_q = qp_at(pic, xl, yl), qp_p = qp_at(pic, xl - 1, yl);
+      int s[4][8];
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[l][i] = px[4 * seg + l][i];
+      if (CIDX == 0) filter_luma_segment(s, qp_p, qp_q, beta_off2, tc_off2);
+      else filter_chroma_segment(s, qp_p, qp_q, c_qp_off, tc_off2);
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) px[4 * seg + l][i] = s[l][i];
+      changed = true;
+    }
+  }
+  // ---- horizontal edge at y = 8j on the vertically filtered samples ----------------------------------
+  if (has_top && has_bottom) {
+    const int yl = (8 * j) << SUB;
+#pragma unroll
+    for (int seg = 0; seg < 2; seg++) {
+      if (seg == 0 ? !has_left : !has_right) continue;
+      const int xl = (x0 + 4 * seg) << SUB;
+      const int lg = tu_log2_at(pic, xl, yl);
+      if (yl & ((1 << lg) - 1)) continue;
+      const int qp_q = qp_at(pic, xl, yl), qp_p = qp_at(pic, xl, yl - 1);
+      int s[4][8];
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) s[l][i] = px[i][4 * seg + l];
+      if (CIDX == 0) filter_luma_segment(s, qp_p, qp_q, beta_off2, tc_off2);
+      else filter_chroma_segment(s, qp_p, qp_q, c_qp_off, tc_off2);
+#pragma unroll
+      for (int l = 0; l < 4; l++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) px[i][4 * seg + l] = s[l][i];
+      changed = true;
+    }
+  }
+  if (!changed) return;
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    const bool row_ok = r < 4 ? has_top : has_bottom;
+    if (!row_ok) continue;
+    uint8_t* row = plane + (size_t)(y0 + r) * pitch;
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a |= (uint32_t)px[r][i] << (8 * i);
+      b |= (uint32_t)px[r][4 + i] << (8 * i);
+    }
+    if (has_left) *reinterpret_cast<uint32_t*>(row + x0) = a;
+    if (has_right) *reinterpret_cast<uint32_t*>(row + x0 + 4) = b;
+  }
+}
+
+// grid: flat over (tile, cell row of the three stacked planes, block of cell columns)
+__global__ void __launch_bounds__(128) deblock_kernel(Arenas A, uint32_t rows, uint32_t xblocks) {
+  const uint32_t per_tile = rows * xblocks;
+  const uint32_t tile = blockIdx.x / per_tile, rem = blockIdx.x % per_tile;
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+  if (A.status[tile].code != 0 || tp->deblock_disabled) return;
+  const int k = (int)((rem % xblocks) * blockDim.x + threadIdx.x);
+  int j = (int)(rem / xblocks);
+  const int rows_y = (pp->h >> 3) + 1, rows_c = pp->chroma ? (((pp->h >> 1) + 7) >> 3) + 1 : 0;
+  int cidx = 0;
+  if (j >= rows_y) {
+    j -= rows_y;
+    cidx = 1;
+    if (j >= rows_c) {
+      j -= rows_c;
+      cidx = 2;
+      if (j >= rows_c) return;
+    }
+  }
+  Pic pic;
+  pic.tu_map = A.tu_map + tp->tu_off;
+  pic.qp_map = A.qp_map + tp->map8_off;
+  pic.w8 = pp->w8;
+  pic.log2_ctb = pp->log2_ctb;
+  pic.wctb = pp->wctb;
+  const int beta_off2 = tp->beta_offset_div2 * 2, tc_off2 = tp->tc_offset_div2 * 2;
+  if (cidx == 0) {
+    if (k > (pp->w >> 3)) return;
+    deblock_cell<0>(pic, A.recon + tp->plane_off[0], pp->pitch_y, pp->w, pp->h, k, j, beta_off2, tc_off2, 0);
+  } else {
+    const int pw = pp->w >> 1, ph = pp->h >> 1;
+    if (k > ((pw + 7) >> 3)) return;
+    if (8 * k - 4 >= pw || 8 * j - 4 >= ph) return;
+    deblock_cell<1>(pic, A.recon + tp->plane_off[cidx], pp->pitch_c, pw, ph, k, j, beta_off2, tc_off2,
+                    cidx == 1 ? pp->pps_cb_qp_offset : pp->pps_cr_qp_offset);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream) {
+  if (!A.n_tiles) return cudaSuccess;
+  const uint32_t cells_x = (max_w >> 3) + 1;
+  const uint32_t rows = ((max_h >> 3) + 1) + 2 * ((((max_h >> 1) + 7) >> 3) + 1);
+  const uint32_t xblocks = (cells_x + 127) / 128;
+  deblock_kernel<<<A.n_tiles * rows * xblocks, 128, 0, stream>>>(A, rows, xblocks);
+  return cudaGetLastError();
+}
+
+}  // namespace dev
+}  // namespace heic

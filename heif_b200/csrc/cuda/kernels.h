@@ -1,0 +1,50 @@
+// Launchers of the sm_100a kernels (one translation unit per stage).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dev_types.h"
+
+namespace heic {
+namespace dev {
+
+struct CabacTabs;
+
+// Stage 1 — CABAC: slice data -> tu_map / TransCoeffLevel / QpY / SAO parameters.
+// order: n_groups * tiles_per_cta tile indices (0xffffffff = idle lane); all tiles of one group share
+// their PicParams geometry.  n_slots = row slots (warps) per CTA.
+size_t cabac_smem_bytes(int tiles_per_cta, int n_slots);
+cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,
+                         int tiles_per_cta, int n_slots, cudaStream_t stream);
+
+// Stage 2 — scaling (8.6.4.2) + inverse DST/DCT (8.6.4.2), in place on the coefficient arena.
+cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, cudaStream_t stream);
+
+// Stage 3 — intra prediction + reconstruction (8.4.4.2), CTU wavefront per picture.
+cudaError_t launch_intra(const Arenas& A, int max_log2_ctb, int n_slots, cudaStream_t stream);
+
+// Stage 4 — deblocking (8.7.2), in place on the reconstruction arena.
+cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream);
+
+// Stage 5 — SAO (8.7.3): recon arena -> final arena.
+cudaError_t launch_sao(const Arenas& A, uint32_t max_pitch, uint32_t max_h, cudaStream_t stream);
+
+// Stage 6 — YCbCr 4:2:0 -> RGB8 + grid stitch + crop (+ irot).
+struct ColorJob {
+  const uint8_t* planes;        // tile t: planes + t * tile_stride; Y then Cb then Cr
+  uint64_t tile_stride;         // bytes between tiles
+  uint64_t cb_off, cr_off;      // offsets of Cb / Cr inside a tile
+  uint32_t pitch_y, pitch_c;
+  uint32_t tile_w, tile_h;      // decoded picture size of a tile
+  uint32_t grid_cols, grid_rows;
+  uint32_t out_w, out_h;        // canvas (before rotation)
+  uint32_t n_images;            // images are consecutive groups of grid_cols*grid_rows tiles
+  uint32_t chroma;              // 0: monochrome (Cb = Cr = 128)
+  uint32_t full_range, matrix_coeffs;
+  uint32_t rotation;            // ccw quarter turns applied to the output
+  uint8_t* rgb;
+  uint64_t pitch, image_stride; // output layout in bytes
+};
+cudaError_t launch_color(const ColorJob& job, cudaStream_t stream);
+
+}  // namespace dev
+}  // namespace heic

@@ -1,0 +1,695 @@
+// Host side of the GPU path: resident batches (bitstreams + descriptors + every intermediate in HBM),
+// stage sequencing on one CUDA stream, and the C ABI of include/heic_b200.h for everything that touches
+// the device.  This is the replacement for the tile loop of HeicDecoder::decode
+// (reference src/heic/decoder.rs:98-119) and SliceSegmentReader::read_data (src/hevc/slice.rs:206).
+// There is no CPU fallback: without a usable CUDA device every entry point fails with HEIC_E_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../host/capi_common.h"
+#include "../host/heic_decoder.h"
+#include "cabac_tables.h"
+#include "host_params.h"
+#include "kernels.h"
+
+using namespace heic;
+using namespace heic::dev;
+
+namespace {
+
+[[noreturn]] void cuda_fail(cudaError_t e, const char* what) {
+  int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? HEIC_E_NO_DEVICE
+             : (e == cudaErrorMemoryAllocation)                                                          ? HEIC_E_NOMEM
+                                                                                                         : HEIC_E_CUDA;
+  bail(code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                               \
+  do {                                         \
+    cudaError_t e__ = (call);                  \
+    if (e__ != cudaSuccess) cuda_fail(e__, #call); \
+  } while (0)
+
+// Growable device / pinned-host buffers: decode_grids re-uses one scratch batch per context, so steady
+// state calls do not allocate.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    CU(cudaMalloc(&p, want));
+    cap = want;
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 8 + 256;
+    CU(cudaMallocHost(&p, want));
+    cap = want;
+  }
+  ~PinnedBuf() {
+    if (p) cudaFreeHost(p);
+  }
+};
+
+size_t up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int env_int(const char* name, int dflt) {
+  const char* s = std::getenv(name);
+  return (s && *s) ? std::atoi(s) : dflt;
+}
+
+}  // namespace
+
+struct heic_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  CabacTabs* d_tabs = nullptr;
+  uint64_t launches = 0;
+  int cabac_tiles_per_cta = 32;  // 32: thread per substream, 1: warp per substream
+  int cabac_slots = 0;           // 0: derive from the picture geometry
+  std::unique_ptr<heic_b200_batch> scratch;
+  ~heic_b200_ctx();
+};
+
+struct ImageInfo {
+  uint32_t first_tile, n_tiles, pic;
+  uint32_t grid_rows, grid_cols, out_w, out_h, rot_w, rot_h, rotation;
+  uint32_t full_range, matrix_coeffs;
+};
+
+struct CabacClass {  // tiles launched together: same wavefront shape
+  int n_slots;
+  uint32_t order_off, n_groups;
+};
+
+struct heic_b200_batch {
+  heic_b200_ctx* ctx = nullptr;
+  bool apply_transforms = false;
+  std::vector<PicParams> pics;
+  std::vector<ScalingSet> scaling;
+  std::vector<TileParams> tiles;
+  std::vector<ImageInfo> images;
+  std::vector<uint32_t> substreams, order;
+  std::vector<CabacClass> classes;
+  size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0;
+  size_t rgb_pitch = 0, rgb_image_stride = 0;
+  uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
+  int max_log2_ctb = 4, intra_slots = 1;
+  uint32_t stages_run = 0;
+  PinnedBuf h_bitstream, h_status;
+  DevBuf d_bitstream, d_substreams, d_order, d_pics, d_tiles, d_scaling, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
+      d_qp, d_sao, d_status, d_rgb;
+  Arenas arenas() const {
+    Arenas a;
+    a.bitstream = (const uint8_t*)d_bitstream.p;
+    a.substreams = (const uint32_t*)d_substreams.p;
+    a.pics = (const PicParams*)d_pics.p;
+    a.tiles = (const TileParams*)d_tiles.p;
+    a.scaling = (const ScalingSet*)d_scaling.p;
+    a.tu_map = (uint32_t*)d_tu.p;
+    a.coeff = (int16_t*)d_coeff.p;
+    a.recon = (uint8_t*)d_recon.p;
+    a.final_ = (uint8_t*)d_final.p;
+    a.ipm = (uint8_t*)d_ipm.p;
+    a.ct_depth = (uint8_t*)d_ctd.p;
+    a.qp_map = (uint8_t*)d_qp.p;
+    a.sao = (uint32_t*)d_sao.p;
+    a.status = (TileStatusDev*)d_status.p;
+    a.n_tiles = (uint32_t)tiles.size();
+    return a;
+  }
+  void load(const heic_image_desc* imgs, uint32_t n_imgs, bool with_rgb);
+  void run(uint32_t mask);
+};
+
+heic_b200_ctx::~heic_b200_ctx() {
+  scratch.reset();
+  if (d_tabs) cudaFree(d_tabs);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ---- batch construction --------------------------------------------------------------------------------
+void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool with_rgb) {
+  pics.clear();
+  scaling.clear();
+  tiles.clear();
+  images.clear();
+  substreams.clear();
+  order.clear();
+  classes.clear();
+  bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = 0;
+  max_tu = max_w = max_h = max_pitch = 0;
+  max_log2_ctb = 4;
+  intra_slots = 1;
+  stages_run = 0;
+  size_t max_rgb_bytes = 0, max_rgb_pitch = 0;
+  for (uint32_t i = 0; i < n_imgs; i++) {
+    const heic_image_desc& im = imgs[i];
+    if (!im.tiles || im.n_tiles == 0 || im.n_tiles != im.grid_rows * im.grid_cols)
+      bail(HEIC_E_INVALID_ARG, "image descriptor: n_tiles must equal grid_rows * grid_cols");
+    PicParams pp;
+    make_pic_params(im.sps, im.pps, pp);
+    ScalingSet ss;
+    build_scaling_set(im.sps, im.pps, ss);
+    size_t s = 0;
+    for (; s < scaling.size(); s++)
+      if (!std::memcmp(&scaling[s], &ss, sizeof ss)) break;
+    if (s == scaling.size()) scaling.push_back(ss);
+    pp.scaling_set = (int)s;
+    // consecutive images with identical parameters share one PicParams entry
+    if (pics.empty() || std::memcmp(&pics.back(), &pp, sizeof pp)) pics.push_back(pp);
+    const uint32_t pic = (uint32_t)pics.size() - 1;
+    ImageInfo info;
+    info.first_tile = (uint32_t)tiles.size();
+    info.n_tiles = im.n_tiles;
+    info.pic = pic;
+    info.grid_rows = im.grid_rows;
+    info.grid_cols = im.grid_cols;
+    info.out_w = im.output_width ? im.output_width : im.grid_cols * (uint32_t)pp.w;
+    info.out_h = im.output_height ? im.output_height : im.grid_rows * (uint32_t)pp.h;
+    if (info.out_w > im.grid_cols * (uint32_t)pp.w || info.out_h > im.grid_rows * (uint32_t)pp.h)
+      bail(HEIC_E_BITSTREAM, "grid canvas is larger than the tile mosaic");
+    info.rotation = apply_transforms ? (im.rotation_ccw_quarter_turns & 3u) : 0u;
+    info.rot_w = (info.rotation & 1u) ? info.out_h : info.out_w;
+    info.rot_h = (info.rotation & 1u) ? info.out_w : info.out_h;
+    info.full_range = im.sps.vui_parameters_present_flag ? im.sps.video_full_range_flag : 0u;
+    info.matrix_coeffs = im.sps.vui_parameters_present_flag ? im.sps.matrix_coeffs : 2u;
+    images.push_back(info);
+    const size_t pitch = up((size_t)info.rot_w * 3, 16);
+    max_rgb_pitch = std::max(max_rgb_pitch, pitch);
+    max_rgb_bytes = std::max(max_rgb_bytes, pitch * info.rot_h);
+    const int ctb4 = 1 << (pp.log2_ctb - 2);
+    for (uint32_t t = 0; t < im.n_tiles; t++) {
+      TileParams tp;
+      std::memset(&tp, 0, sizeof tp);
+      make_tile_params(pp, im.pps, im.tiles[t], tp);
+      tp.pic = pic;
+      tp.image = i;
+      tp.tile_in_image = t;
+      tp.bs_off = (uint32_t)bs_bytes;
+      bs_bytes = up(bs_bytes + tp.bs_len + 8, 16);
+      if (bs_bytes > 0xfff00000ull) bail(HEIC_E_UNSUPPORTED, "more than 4 GiB of slice data in one batch");
+      tp.sub_first = (uint32_t)substreams.size();
+      for (uint32_t k = 0; k < tp.n_sub; k++) substreams.push_back(im.tiles[t].header.substream_offset[k]);
+      tp.tu_off = tu_words;
+      tu_words += (size_t)pp.n_tu;
+      tp.coeff_off[0] = coeff_elems;
+      tp.coeff_off[1] = tp.coeff_off[0] + (size_t)pp.n_tu * 16;
+      tp.coeff_off[2] = tp.coeff_off[1] + (size_t)pp.n_tu * 4;
+      coeff_elems = tp.coeff_off[2] + (size_t)pp.n_tu * 4;
+      // planes cover whole CTBs so the intra kernel never needs a store mask beyond the picture size
+      const size_t ysz = (size_t)pp.pitch_y * (size_t)pp.h, csz = (size_t)pp.pitch_c * (size_t)(pp.h >> 1);
+      tp.plane_off[0] = plane_bytes;
+      tp.plane_off[1] = tp.plane_off[0] + ysz;
+      tp.plane_off[2] = tp.plane_off[1] + csz;
+      plane_bytes = up(tp.plane_off[2] + csz, 256);
+      tp.map4_off = map4_bytes;
+      map4_bytes = up(map4_bytes + (size_t)pp.w4 * pp.h4, 64);
+      tp.map8_off = map8_bytes;
+      map8_bytes = up(map8_bytes + (size_t)pp.w8 * pp.h8, 64);
+      tp.sao_off = sao_words;
+      sao_words += (size_t)pp.wctb * pp.hctb * 4;
+      tiles.push_back(tp);
+      (void)ctb4;
+    }
+    max_tu = std::max(max_tu, (uint32_t)pp.n_tu);
+    max_w = std::max(max_w, (uint32_t)pp.w);
+    max_h = std::max(max_h, (uint32_t)pp.h);
+    max_pitch = std::max(max_pitch, (uint32_t)pp.pitch_y);
+    max_log2_ctb = std::max(max_log2_ctb, pp.log2_ctb);
+    intra_slots = std::max(intra_slots, std::min(8, std::min(pp.hctb, (pp.wctb + 1) / 2 + 1)));
+  }
+  rgb_pitch = max_rgb_pitch;
+  rgb_image_stride = up(max_rgb_bytes, 256);
+
+  // ---- CABAC launch classes: tiles with the same wavefront shape, heaviest first, TILES per CTA ----------
+  const int tpc = ctx->cabac_tiles_per_cta;
+  std::map<std::tuple<int, int, int, int>, std::vector<uint32_t>> by_shape;
+  for (uint32_t t = 0; t < tiles.size(); t++) {
+    const PicParams& pp = pics[tiles[t].pic];
+    by_shape[std::make_tuple(pp.wpp, pp.wctb, pp.hctb, pp.log2_ctb)].push_back(t);
+  }
+  for (auto& kv : by_shape) {
+    std::vector<uint32_t>& v = kv.second;
+    std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tiles[a].bs_len > tiles[b].bs_len; });
+    const int wpp = std::get<0>(kv.first), wctb = std::get<1>(kv.first), hctb = std::get<2>(kv.first);
+    CabacClass c;
+    // with the two-CTU WPP lag at most ceil(wctb / 2) rows of a picture are in flight
+    c.n_slots = wpp ? std::max(1, std::min(hctb, (wctb + 1) / 2)) : 1;
+    if (ctx->cabac_slots > 0 && wpp) c.n_slots = std::min(hctb, ctx->cabac_slots);
+    c.n_slots = std::min(c.n_slots, tpc == 32 ? 8 : 16);
+    c.order_off = (uint32_t)order.size();
+    c.n_groups = (uint32_t)((v.size() + tpc - 1) / tpc);
+    for (uint32_t g = 0; g < c.n_groups; g++)
+      for (int l = 0; l < tpc; l++) {
+        size_t idx = (size_t)g * tpc + l;
+        order.push_back(idx < v.size() ? v[idx] : 0xffffffffu);
+      }
+    classes.push_back(c);
+  }
+
+  // ---- device memory + uploads -----------------------------------------------------------------------
+  cudaStream_t st = ctx->stream;
+  h_bitstream.ensure(bs_bytes + 16);
+  std::memset(h_bitstream.p, 0, bs_bytes + 16);
+  {
+    size_t t = 0;
+    for (uint32_t i = 0; i < n_imgs; i++)
+      for (uint32_t k = 0; k < imgs[i].n_tiles; k++, t++)
+        std::memcpy((uint8_t*)h_bitstream.p + tiles[t].bs_off, imgs[i].tiles[k].rbsp, imgs[i].tiles[k].rbsp_len);
+  }
+  d_bitstream.ensure(bs_bytes + 16);
+  d_substreams.ensure(substreams.size() * 4);
+  d_order.ensure(order.size() * 4);
+  d_pics.ensure(pics.size() * sizeof(PicParams));
+  d_tiles.ensure(tiles.size() * sizeof(TileParams));
+  d_scaling.ensure(scaling.size() * sizeof(ScalingSet));
+  d_tu.ensure(tu_words * 4);
+  d_coeff.ensure(coeff_elems * 2);
+  d_recon.ensure(plane_bytes);
+  d_final.ensure(plane_bytes);
+  d_ipm.ensure(map4_bytes);
+  d_ctd.ensure(map8_bytes);
+  d_qp.ensure(map8_bytes);
+  d_sao.ensure(sao_words * 4);
+  d_status.ensure(tiles.size() * sizeof(TileStatusDev));
+  h_status.ensure(tiles.size() * sizeof(TileStatusDev));
+  if (with_rgb) d_rgb.ensure(rgb_image_stride * images.size());
+  CU(cudaMemcpyAsync(d_bitstream.p, h_bitstream.p, bs_bytes + 16, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_substreams.p, substreams.data(), substreams.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_pics.p, pics.data(), pics.size() * sizeof(PicParams), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(TileParams), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_scaling.p, scaling.data(), scaling.size() * sizeof(ScalingSet), cudaMemcpyHostToDevice, st));
+  // the host vectors above are pageable: the copies have completed (staged) when cudaMemcpyAsync returns
+}
+
+// ---- stage sequencing ----------------------------------------------------------------------------------
+void heic_b200_batch::run(uint32_t mask) {
+  cudaStream_t st = ctx->stream;
+  const Arenas A = arenas();
+  if (!A.n_tiles) return;
+  if (mask & HEIC_STAGE_CABAC) {
+    // tu_map must be zero outside transform-unit origins, levels zero outside significant coefficients
+    CU(cudaMemsetAsync(d_tu.p, 0, tu_words * 4, st));
+    CU(cudaMemsetAsync(d_coeff.p, 0, coeff_elems * 2, st));
+    CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
+    for (const CabacClass& c : classes) {
+      CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)d_order.p + c.order_off, c.n_groups, ctx->cabac_tiles_per_cta,
+                      c.n_slots, st));
+      ctx->launches++;
+    }
+  }
+  if (mask & HEIC_STAGE_TRANSFORM) {
+    CU(launch_transform(A, max_tu, st));
+    ctx->launches++;
+  }
+  if (mask & HEIC_STAGE_INTRA) {
+    CU(launch_intra(A, max_log2_ctb, intra_slots, st));
+    ctx->launches++;
+  }
+  if (mask & HEIC_STAGE_DEBLOCK) {
+    CU(launch_deblock(A, max_w, max_h, st));
+    ctx->launches++;
+  }
+  if (mask & HEIC_STAGE_SAO) {
+    CU(launch_sao(A, max_pitch, max_h, st));
+    ctx->launches++;
+  }
+  if ((mask & HEIC_STAGE_COLOR) && d_rgb.p) {
+    // consecutive images of identical geometry go out in one launch
+    size_t i = 0;
+    while (i < images.size()) {
+      size_t j = i + 1;
+      auto same = [&](const ImageInfo& a, const ImageInfo& b) {
+        return a.pic == b.pic && a.n_tiles == b.n_tiles && a.grid_cols == b.grid_cols && a.out_w == b.out_w &&
+               a.out_h == b.out_h && a.rotation == b.rotation && a.full_range == b.full_range &&
+               a.matrix_coeffs == b.matrix_coeffs;
+      };
+      while (j < images.size() && same(images[i], images[j])) j++;
+      const ImageInfo& im = images[i];
+      const PicParams& pp = pics[im.pic];
+      const TileParams& t0 = tiles[im.first_tile];
+      ColorJob job;
+      job.planes = (const uint8_t*)d_final.p + t0.plane_off[0];
+      job.tile_stride = im.n_tiles > 1 || j - i > 1
+                            ? (size_t)(tiles[std::min<size_t>(im.first_tile + 1, tiles.size() - 1)].plane_off[0] - t0.plane_off[0])
+                            : 0;
+      job.cb_off = t0.plane_off[1] - t0.plane_off[0];
+      job.cr_off = t0.plane_off[2] - t0.plane_off[0];
+      job.pitch_y = (uint32_t)pp.pitch_y;
+      job.pitch_c = (uint32_t)pp.pitch_c;
+      job.tile_w = (uint32_t)pp.w;
+      job.tile_h = (uint32_t)pp.h;
+      job.grid_cols = im.grid_cols;
+      job.grid_rows = im.grid_rows;
+      job.out_w = im.out_w;
+      job.out_h = im.out_h;
+      job.n_images = (uint32_t)(j - i);
+      job.chroma = (uint32_t)pp.chroma;
+      job.full_range = im.full_range;
+      job.matrix_coeffs = im.matrix_coeffs;
+      job.rotation = im.rotation;
+      job.rgb = (uint8_t*)d_rgb.p + i * rgb_image_stride;
+      job.pitch = rgb_pitch;
+      job.image_stride = rgb_image_stride;
+      CU(launch_color(job, st));
+      ctx->launches++;
+      i = j;
+    }
+  }
+  stages_run |= mask;
+}
+
+// ---- C ABI ---------------------------------------------------------------------------------------------
+namespace {
+
+void collect_status(heic_b200_batch* b, heic_tile_status* status) {
+  cudaStream_t st = b->ctx->stream;
+  const size_t n = b->tiles.size();
+  CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, n * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  const TileStatusDev* s = (const TileStatusDev*)b->h_status.p;
+  for (size_t i = 0; i < n; i++) {
+    status[i].code = s[i].code;
+    status[i].bins_decoded = s[i].bins;
+    status[i].ctus_decoded = s[i].ctus;
+    status[i].reserved = 0;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!out_ctx) bail(HEIC_E_INVALID_ARG, "null argument");
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      bail(HEIC_E_NO_DEVICE, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    auto c = std::make_unique<heic_b200_ctx>();
+    if (device < 0) CU(cudaGetDevice(&c->device));
+    else c->device = device;
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 10)
+      bail(HEIC_E_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 class; the kernels are built for sm_100a only");
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    static CabacTabs tabs;
+    build_cabac_tabs(tabs);
+    CU(cudaMalloc((void**)&c->d_tabs, sizeof(CabacTabs)));
+    CU(cudaMemcpy(c->d_tabs, &tabs, sizeof tabs, cudaMemcpyHostToDevice));
+    c->cabac_tiles_per_cta = env_int("HEIC_B200_CABAC_TILES_PER_CTA", 32) == 1 ? 1 : 32;
+    c->cabac_slots = env_int("HEIC_B200_CABAC_SLOTS", 0);
+    *out_ctx = c.release();
+    return 0;
+  }));
+}
+
+void heic_b200_destroy(heic_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  delete ctx;
+}
+
+uint64_t heic_b200_launch_count(const heic_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, heic_b200_batch** out) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!ctx || !imgs || !out || !n_imgs) bail(HEIC_E_INVALID_ARG, "null argument");
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    auto b = std::make_unique<heic_b200_batch>();
+    b->ctx = ctx;
+    b->apply_transforms = false;
+    b->load(imgs, n_imgs, true);
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = b.release();
+    return 0;
+  }));
+}
+
+void heic_b200_batch_destroy(heic_b200_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  delete b;
+}
+
+int32_t heic_b200_batch_run_stages(heic_b200_batch* b, uint32_t stage_mask) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b) bail(HEIC_E_INVALID_ARG, "null batch");
+    CU(cudaSetDevice(b->ctx->device));
+    b->run(stage_mask & HEIC_STAGE_ALL);
+    return 0;
+  }));
+}
+
+int32_t heic_b200_batch_decode(heic_b200_batch* b) { return heic_b200_batch_run_stages(b, HEIC_STAGE_ALL); }
+
+int32_t heic_b200_batch_sync(heic_b200_batch* b) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b) bail(HEIC_E_INVALID_ARG, "null batch");
+    CU(cudaStreamSynchronize(b->ctx->stream));
+    return 0;
+  }));
+}
+
+void* heic_b200_batch_stream(heic_b200_batch* b) { return b ? (void*)b->ctx->stream : nullptr; }
+
+int32_t heic_b200_batch_rgb(heic_b200_batch* b, void** dev_ptr, size_t* pitch, size_t* image_stride) {
+  if (!b) {
+    set_last_error("null batch");
+    return HEIC_E_INVALID_ARG;
+  }
+  if (dev_ptr) *dev_ptr = b->d_rgb.p;
+  if (pitch) *pitch = b->rgb_pitch;
+  if (image_stride) *image_stride = b->rgb_image_stride;
+  return 0;
+}
+
+int32_t heic_b200_batch_download_rgb(heic_b200_batch* b, uint8_t* rgb_out, size_t pitch, size_t image_stride) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b || !rgb_out) bail(HEIC_E_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    for (size_t i = 0; i < b->images.size(); i++) {
+      const ImageInfo& im = b->images[i];
+      if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+      CU(cudaMemcpy2DAsync(rgb_out + i * image_stride, pitch, (const uint8_t*)b->d_rgb.p + i * b->rgb_image_stride,
+                           b->rgb_pitch, (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+  }));
+}
+
+int32_t heic_b200_batch_status(heic_b200_batch* b, heic_tile_status* status) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b || !status) bail(HEIC_E_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(b->ctx->device));
+    collect_status(b, status);
+    return 0;
+  }));
+}
+
+uint32_t heic_b200_batch_tile_count(const heic_b200_batch* b) { return b ? (uint32_t)b->tiles.size() : 0; }
+
+int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_tile_dump* dump) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b || !dump || tile_index >= b->tiles.size()) bail(HEIC_E_INVALID_ARG, "invalid argument");
+    CU(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    CU(cudaStreamSynchronize(st));
+    const TileParams& tp = b->tiles[tile_index];
+    const PicParams& pp = b->pics[tp.pic];
+    if (dump->tu_map) {
+      if (dump->tu_map_len < (uint32_t)pp.n_tu) bail(HEIC_E_INVALID_ARG, "tu_map buffer too small");
+      CU(cudaMemcpy(dump->tu_map, (const uint32_t*)b->d_tu.p + tp.tu_off, (size_t)pp.n_tu * 4, cudaMemcpyDeviceToHost));
+    }
+    for (int c = 0; c < (pp.chroma ? 3 : 1); c++)
+      if (dump->coeff[c]) {
+        const size_t n = (size_t)pp.n_tu * (c ? 4 : 16);
+        if (dump->coeff_len[c] < n) bail(HEIC_E_INVALID_ARG, "coefficient buffer too small");
+        CU(cudaMemcpy(dump->coeff[c], (const int16_t*)b->d_coeff.p + tp.coeff_off[c], n * 2, cudaMemcpyDeviceToHost));
+      }
+    if (dump->qp_map) {
+      const size_t wq = (size_t)pp.w >> 3, hq = (size_t)pp.h >> 3;
+      if (dump->qp_map_len < wq * hq) bail(HEIC_E_INVALID_ARG, "qp_map buffer too small");
+      CU(cudaMemcpy2D(dump->qp_map, wq, (const uint8_t*)b->d_qp.p + tp.map8_off, (size_t)pp.w8, wq, hq, cudaMemcpyDeviceToHost));
+    }
+    if (dump->sao) {
+      const size_t n = (size_t)pp.wctb * pp.hctb * 4;
+      if (dump->sao_len < n) bail(HEIC_E_INVALID_ARG, "sao buffer too small");
+      CU(cudaMemcpy(dump->sao, (const uint32_t*)b->d_sao.p + tp.sao_off, n * 4, cudaMemcpyDeviceToHost));
+    }
+    const uint8_t* src = (const uint8_t*)((b->stages_run & HEIC_STAGE_SAO) ? b->d_final.p : b->d_recon.p);
+    for (int c = 0; c < (pp.chroma ? 3 : 1); c++)
+      if (dump->plane[c]) {
+        const size_t w = (size_t)pp.w >> (c ? 1 : 0), h = (size_t)pp.h >> (c ? 1 : 0);
+        if (dump->plane_len[c] < w * h) bail(HEIC_E_INVALID_ARG, "plane buffer too small");
+        CU(cudaMemcpy2D(dump->plane[c], w, src + tp.plane_off[c], (size_t)(c ? pp.pitch_c : pp.pitch_y), w, h,
+                        cudaMemcpyDeviceToHost));
+      }
+    return 0;
+  }));
+}
+
+// HOST in / HOST out: the reference-facing call (replaces the tile loop of decoder.rs:98-119).
+static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
+                                 size_t pitch, size_t image_stride, int32_t apply_transforms, uint8_t* y_out,
+                                 uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
+  if (!ctx || !imgs || !n_imgs) bail(HEIC_E_INVALID_ARG, "null argument");
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->scratch) {
+    ctx->scratch = std::make_unique<heic_b200_batch>();
+    ctx->scratch->ctx = ctx;
+  }
+  heic_b200_batch* b = ctx->scratch.get();
+  b->apply_transforms = apply_transforms != 0;
+  b->load(imgs, n_imgs, rgb_out != nullptr);
+  cudaStream_t st = ctx->stream;
+  b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
+  if (rgb_out) {
+    for (size_t i = 0; i < b->images.size(); i++) {
+      const ImageInfo& im = b->images[i];
+      if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+      CU(cudaMemcpy2DAsync(rgb_out + i * image_stride, pitch, (const uint8_t*)b->d_rgb.p + i * b->rgb_image_stride,
+                           b->rgb_pitch, (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, st));
+    }
+  } else {
+    // planar output: tile mosaic cropped to the canvas, images back to back
+    size_t yo = 0, co = 0;
+    for (size_t i = 0; i < b->images.size(); i++) {
+      const ImageInfo& im = b->images[i];
+      const PicParams& pp = b->pics[im.pic];
+      const size_t cw = (im.out_w + 1) / 2, chh = (im.out_h + 1) / 2;
+      for (uint32_t t = 0; t < im.n_tiles; t++) {
+        const TileParams& tp = b->tiles[im.first_tile + t];
+        const size_t tx = (size_t)(t % im.grid_cols) * pp.w, ty = (size_t)(t / im.grid_cols) * pp.h;
+        if (tx >= im.out_w || ty >= im.out_h) continue;
+        const size_t w = std::min<size_t>(pp.w, im.out_w - tx), h = std::min<size_t>(pp.h, im.out_h - ty);
+        CU(cudaMemcpy2DAsync(y_out + yo + ty * im.out_w + tx, im.out_w, (const uint8_t*)b->d_final.p + tp.plane_off[0],
+                             pp.pitch_y, w, h, cudaMemcpyDeviceToHost, st));
+        if (pp.chroma && cb_out && cr_out) {
+          const size_t wc = std::min<size_t>(pp.w / 2, cw - tx / 2), hc = std::min<size_t>(pp.h / 2, chh - ty / 2);
+          CU(cudaMemcpy2DAsync(cb_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[1],
+                               pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
+          CU(cudaMemcpy2DAsync(cr_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[2],
+                               pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
+        }
+      }
+      yo += (size_t)im.out_w * im.out_h;
+      co += cw * chh;
+    }
+  }
+  std::vector<heic_tile_status> local;
+  heic_tile_status* s = status;
+  if (!s) {
+    local.resize(b->tiles.size());
+    s = local.data();
+  }
+  collect_status(b, s);  // synchronises the stream
+  int bad = 0;
+  for (size_t i = 0; i < b->tiles.size(); i++)
+    if (s[i].code != 0) bad++;
+  if (bad) {
+    set_last_error(std::to_string(bad) + " tile(s) failed to decode (malformed slice data); see the per-tile status");
+    return HEIC_E_BITSTREAM;
+  }
+  return 0;
+}
+
+int32_t heic_b200_decode_grids(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
+                               size_t pitch, size_t image_stride, int32_t apply_transforms, heic_tile_status* status) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!rgb_out) bail(HEIC_E_INVALID_ARG, "null output buffer");
+    return decode_grids_impl(ctx, imgs, n_imgs, rgb_out, pitch, image_stride, apply_transforms, nullptr, nullptr, nullptr,
+                             status);
+  }));
+}
+
+int32_t heic_b200_decode_grids_yuv(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* y_out,
+                                   uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!y_out) bail(HEIC_E_INVALID_ARG, "null output buffer");
+    return decode_grids_impl(ctx, imgs, n_imgs, nullptr, 0, 0, 0, y_out, cb_out, cr_out, status);
+  }));
+}
+
+int32_t heic_b200_decode_file(heic_b200_ctx* ctx, const uint8_t* data, size_t len, uint8_t* rgb_out, size_t pitch,
+                              int32_t apply_transforms) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!ctx || !data || !rgb_out) bail(HEIC_E_INVALID_ARG, "null argument");
+    std::unique_ptr<HeicFile> f = HeicDecoder::open(data, len);
+    return decode_grids_impl(ctx, &f->primary.desc, 1, rgb_out, pitch, 0, apply_transforms, nullptr, nullptr, nullptr,
+                             nullptr);
+  }));
+}
+
+int32_t heic_b200_color_stitch(heic_b200_ctx* ctx, const void* dev_planes, uint32_t n_images, uint32_t grid_rows,
+                               uint32_t grid_cols, uint32_t tile_w, uint32_t tile_h, uint32_t out_w, uint32_t out_h,
+                               uint32_t full_range, uint32_t matrix_coeffs, void* dev_rgb, size_t pitch,
+                               size_t image_stride) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!ctx || !dev_planes || !dev_rgb) bail(HEIC_E_INVALID_ARG, "null argument");
+    if (!n_images || !grid_rows || !grid_cols || (tile_w & 7) || (tile_h & 1) || !tile_w || !tile_h)
+      bail(HEIC_E_INVALID_ARG, "tile width must be a multiple of 8 and tile height even");
+    if (out_w > grid_cols * tile_w || out_h > grid_rows * tile_h || pitch < (size_t)out_w * 3)
+      bail(HEIC_E_INVALID_ARG, "canvas larger than the tile mosaic, or pitch too small");
+    CU(cudaSetDevice(ctx->device));
+    ColorJob job;
+    job.planes = (const uint8_t*)dev_planes;
+    job.tile_stride = (size_t)tile_w * tile_h * 3 / 2;
+    job.cb_off = (size_t)tile_w * tile_h;
+    job.cr_off = job.cb_off + (size_t)(tile_w / 2) * (tile_h / 2);
+    job.pitch_y = tile_w;
+    job.pitch_c = tile_w / 2;
+    job.tile_w = tile_w;
+    job.tile_h = tile_h;
+    job.grid_cols = grid_cols;
+    job.grid_rows = grid_rows;
+    job.out_w = out_w;
+    job.out_h = out_h;
+    job.n_images = n_images;
+    job.chroma = 1;
+    job.full_range = full_range;
+    job.matrix_coeffs = matrix_coeffs;
+    job.rotation = 0;
+    job.rgb = (uint8_t*)dev_rgb;
+    job.pitch = pitch;
+    job.image_stride = image_stride;
+    CU(launch_color(job, ctx->stream));
+    ctx->launches++;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }));
+}
+
+}  // extern "C"
