@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — decoded MP/s of the HEIC hot path (slice data -> RGB) on a batch of 12 MP 8x6 grid images.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port on all host cores)
+
+A step = one decode of one resident batch of --batch images per GPU (48 tiles of 512x512 each; the images are
+seeded permutations of the 48 real tiles of halfmoonbay.heic, so every image has iPhone bit-rates while tiles
+land on different lanes/SMs).  `value` times K steps with the batch already in HBM (CUDA events on the library's
+stream); `e2e` times the reference-facing C-ABI call heic_b200_decode_grids with HOST descriptors/bitstreams in
+and pinned HOST RGB out.  Work shards by image across ranks with no data-path collective (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FIXTURE = os.path.join(ROOT, "tests", "golden", "halfmoonbay.heic")
+OUT_W, OUT_H = 4032, 3024
+MP_PER_IMAGE = OUT_W * OUT_H / 1e6
+CODED_SAMPLES_PER_IMAGE = 48 * 512 * 512 * 3 // 2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_images(heic_file, n_images: int, seed: int):
+    """n_images descriptors whose tiles are seeded permutations of the fixture's 48 tiles."""
+    from heif_b200 import _capi as K
+
+    base = heic_file.primary
+    rng = np.random.default_rng(seed)
+    keep, images = [], []
+    for _ in range(n_images):
+        perm = rng.permutation(base.n_tiles)
+        tiles = (K.TileDesc * base.n_tiles)()
+        for d, s in enumerate(perm):
+            C.memmove(C.byref(tiles, d * C.sizeof(K.TileDesc)), C.byref(base.tiles[int(s)]), C.sizeof(K.TileDesc))
+        im = K.ImageDesc()
+        C.memmove(C.byref(im), C.byref(base), C.sizeof(K.ImageDesc))
+        im.tiles = C.cast(tiles, C.POINTER(K.TileDesc))
+        keep.append(tiles)
+        images.append(im)
+    return images, keep
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0: float, t1: float):
+        if not self.p:
+            return None
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return None
+        try:
+            sm = sorted(float(r[0]) for r in rows)
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+        except ValueError:
+            return None
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/hevc_oracle.c) on the host cores.  kind = "port": the reference is Rust,
+# there is no cargo/rustc in the image, and its slice decoder ends in todo!() anyway ("Oracle").
+# ---------------------------------------------------------------------------------------------------------
+def cpu_decode_images(heic_file, n_images: int, threads: int) -> float:
+    """Decodes n_images x 48 tiles + colour/stitch with `threads` host threads; returns seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle_py
+
+    img = heic_file.primary
+    w, h = img.sps.pic_width_in_luma_samples, img.sps.pic_height_in_luma_samples
+
+    def one(t):
+        td = img.tiles[t % img.n_tiles]
+        r = oracle_py.decode_picture(img.sps, img.pps, td.header, (td.rbsp, td.rbsp_len), intermediates=False)
+        return np.concatenate([p.ravel() for p in r["plane"]])
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        planes = list(ex.map(one, range(n_images * img.n_tiles)))
+        per_image = [np.concatenate(planes[i * img.n_tiles:(i + 1) * img.n_tiles]) for i in range(n_images)]
+        list(ex.map(lambda p: oracle_py.color_stitch(p, img.grid_rows, img.grid_cols, w, h, img.output_width, img.output_height,
+                                                     img.sps.video_full_range_flag, img.sps.matrix_coeffs), per_image))
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import heif_b200
+    from oracle import oracle_py
+
+    oracle_py.load()
+    f = heif_b200.HeicFile(open(FIXTURE, "rb").read())
+    cores = os.cpu_count() or 1
+    n_img = max(1, args.ref_images)
+    for _ in range(args.warmup):
+        cpu_decode_images(f, n_img, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_decode_images(f, n_img, cores)
+    dt = time.perf_counter() - t0
+    value = args.steps * n_img * MP_PER_IMAGE / dt
+    sample = f"{n_img} image(s) = {48 * n_img} real 512x512 tiles of halfmoonbay.heic per step, oracle port (C, -O2), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "decoded MP/s (12MP HEIC grid batch)", "value": round(value, 3), "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "halfmoonbay.heic tiles (real), CPU",
+        "config": {"workload": "12 MP 8x6 grid of 512x512 HEVC intra tiles -> RGB, bounded CPU sample", "images_per_step": n_img},
+        "cpu_baseline": {"value": round(value, 3), "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "296")), help="images per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "64")))
+    ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU arm")
+    ap.add_argument("--cpu-images", type=int, default=4, help="images in the cpu_baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stages", action="store_true", help="also print a per-stage table to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    import heif_b200 as H
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    f = H.HeicFile(open(FIXTURE, "rb").read())
+    dec = H.HeicDecoder(device=local)
+    images, keep = make_images(f, args.batch, seed=1 + rank)
+    batch = dec.batch(images)
+    stream = torch.cuda.ExternalStream(batch.stream, device=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    # ---- value: K steps, batch resident in HBM -----------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        batch.decode()
+    batch.sync()
+    st = batch.status()
+    bad = [i for i in range(batch.n_tiles) if st[i].code != 0]
+    if bad:
+        raise SystemExit(f"{len(bad)} tiles failed to decode")
+    bins_per_step = sum(st[i].bins_decoded for i in range(batch.n_tiles))
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    l0 = dec.launch_count()
+    e0, e1 = ev(), ev()
+    t_wall0 = time.time()
+    e0.record(stream)
+    for _ in range(args.steps):
+        batch.decode()
+    e1.record(stream)
+    batch.sync()
+    barrier()
+    t_wall1 = time.time()
+    launches = dec.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop(t_wall0, t_wall1) if clocks else None
+
+    # ---- per-stage device times (same batch, one stage per event pair) -------------------------------------
+    stage_defs = [("cabac", H.STAGE_CABAC), ("transform", H.STAGE_TRANSFORM), ("intra", H.STAGE_INTRA),
+                  ("deblock", H.STAGE_DEBLOCK), ("sao", H.STAGE_SAO), ("color_stitch", H.STAGE_COLOR)]
+    stage_ms = {n: 0.0 for n, _ in stage_defs}
+    reps = 2
+    for _ in range(reps):
+        evs = [ev() for _ in range(len(stage_defs) + 1)]
+        evs[0].record(stream)
+        for i, (n, m) in enumerate(stage_defs):
+            batch.run(m)
+            evs[i + 1].record(stream)
+        batch.sync()
+        for i, (n, _) in enumerate(stage_defs):
+            stage_ms[n] += evs[i].elapsed_time(evs[i + 1]) / reps
+
+    # coded samples (cbf = 1) for the algorithmic bytes of the transform / intra stages
+    tu = [batch.dump_tile(t)["tu_map"] for t in range(48)]
+    coded = 0
+    for m in tu:
+        o = m[(m & 1) == 1]
+        n2 = (4 << ((o >> 1) & 3)).astype(np.int64) ** 2
+        coded += int((n2 * ((o >> 3) & 1)).sum())
+        nc = np.where(((o >> 1) & 3) == 0, 16, n2 // 4)
+        coded += int((nc * ((o >> 6) & 1) * (((o >> 4) & 1) + ((o >> 5) & 1))).sum())
+    coded_per_image = coded  # every image is a permutation of the same 48 tiles
+    n_img = args.batch
+    a_c = CODED_SAMPLES_PER_IMAGE
+    alg_bytes = {  # per image, SURVEY.md section 8(d)
+        "cabac": 1704187 + 2 * coded_per_image,          # slice data in + TransCoeffLevel out (dense int16 of coded blocks)
+        "transform": 4 * coded_per_image,                 # 2 B in + 2 B out per coded sample
+        "intra": 2 * coded_per_image + a_c,               # residual in + reconstructed planes out
+        "deblock": 2 * a_c,                               # planes in + out
+        "sao": 2 * a_c,
+        "color_stitch": int(4.5 * OUT_W * OUT_H),         # 1.5 B in + 3 B out per output pixel
+    }
+    stages = []
+    for n, _ in stage_defs:
+        gbs = alg_bytes[n] * n_img / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0
+        stages.append({"kernel": n, "ms": round(stage_ms[n], 4), "alg_GB": round(alg_bytes[n] * n_img / 1e9, 4),
+                       "achieved_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
+    dom = max(stages, key=lambda s: s["ms"])
+    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+    cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
+
+    # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
+    eb = min(args.e2e_batch, args.batch)
+    out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8).pin_memory()
+    out_np = out.numpy()
+    h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
+    d2h = eb * OUT_H * OUT_W * 3
+    for _ in range(2):
+        dec.decode_grids(images[:eb], out=out_np)
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dec.decode_grids(images[:eb], out=out_np)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_val = eb * MP_PER_IMAGE / e2e_s
+
+    # ---- aggregate over ranks: max time --------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+        e2e_val = eb * MP_PER_IMAGE / e2e_s
+    value = world * args.steps * n_img * MP_PER_IMAGE / (ms * 1e-3)
+    e2e_total = world * e2e_val
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle_py
+
+        oracle_py.load()
+        cores = os.cpu_count() or 1
+        dt = cpu_decode_images(f, args.cpu_images, cores)
+        cpu = {"value": round(args.cpu_images * MP_PER_IMAGE / dt, 3), "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_images} images = {48 * args.cpu_images} real tiles of halfmoonbay.heic, oracle port (C -O2), {cores} threads, {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "decoded MP/s (12MP HEIC grid batch)", "value": round(value, 2), "unit": "MP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "halfmoonbay.heic's 48 real 512x512 tiles, seeded permutation per image (synthetic batch of real bitstreams)",
+            "config": {"workload": "configs[4] sharded: 12 MP 8x6 grid of 512x512 HEVC intra tiles (WPP, SAO, deblock, scaling lists) -> RGB 4032x3024",
+                       "images_per_gpu_per_step": n_img, "tiles_per_step_per_gpu": n_img * 48, "parallelism": f"image-sharded x{world}, no collective",
+                       "l2": "working set per step >> 126 MB L2 (inputs larger than L2)",
+                       "cabac_tiles_per_cta": int(os.environ.get("HEIC_B200_CABAC_TILES_PER_CTA", "32"))},
+            "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                         "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                         "note": "dominant kernel by time; CABAC is serial-latency bound (see cabac_bins_per_s_per_sm), per-kernel rooflines in `stages`"},
+            "stages": stages,
+            "cabac_bins_per_s_per_sm": round(cabac_bins / n_sm, 1), "cabac_bins_per_image": bins_per_step // n_img,
+            "coded_mp_per_s": round(value * (48 * 512 * 512) / (OUT_W * OUT_H), 2),
+            "cpu_baseline": cpu,
+            "e2e": {"value": round(e2e_total, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "images_per_call": eb, "ms_per_call": round(e2e_s * 1e3, 3)},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+        if args.stages:
+            for s in stages:
+                print(s, file=sys.stderr)
+    batch.close()
+    dec.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -40,12 +40,19 @@ struct SmemSync {
   int n_slots, lane, direct;
 
   __device__ __forceinline__ bool wait(int row, int n) {
+    unsigned ns = 32;
     if (TILES == 1) {
-      while (progress[row] < n && !*aborted) __nanosleep(64);
+      while (progress[row] < n && !*aborted) {
+        __nanosleep(ns);
+        if (ns < 2048) ns *= 2;
+      }
     } else {
       __syncwarp();
       if (lane == 0)
-        while (progress[row] < n) __nanosleep(64);
+        while (progress[row] < n) {
+          __nanosleep(ns);
+          if (ns < 2048) ns *= 2;
+        }
       __syncwarp();
     }
     __threadfence_block();
@@ -76,7 +83,7 @@ struct SmemSync {
 }  // namespace
 
 template <int TILES>
-__global__ void __launch_bounds__(512) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
+__global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? 3 : 1) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
                                                     const uint32_t* __restrict__ order, int n_slots) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
@@ -104,6 +111,7 @@ __global__ void __launch_bounds__(512) cabac_kernel(Arenas A, const CabacTabs* _
   Parser<TILES> P;
   P.T = &sh->tabs;
   P.ctx = ctx_all + (size_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0 : lane);
+  P.ctx_off = (uint32_t)(P.ctx - smem_raw);
   P.pp = pp;
   P.tp = tp;
   P.tu_map = A.tu_map + tp->tu_off;

@@ -36,6 +36,11 @@ struct CabacTabs {
   uint8_t init_value[NUM_CTX_PAD];
 };
 
+#if defined(__CUDACC__)
+#define HEIC_NO_UNROLL _Pragma("unroll 1")
+#else
+#define HEIC_NO_UNROLL
+#endif
 #if defined(__CUDA_ARCH__)
 #define HEIC_CLZ(x) __clz(x)
 #else
@@ -50,50 +55,77 @@ HEIC_HD uint32_t compact1by1(uint32_t v) {  // even bits of an 8-bit z-order ind
   return v;
 }
 
+#if defined(__CUDA_ARCH__)
+// All dynamically indexed parser state (tables, context tables) lives in the kernel's dynamic shared memory;
+// going through this symbol instead of generic pointers lets the compiler emit LDS/STS.
+extern __shared__ __align__(16) unsigned char heic_cabac_smem[];
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // Arithmetic decoding engine (9.3.4.3).  `val` holds ivlOffset << 22 with up to 22 look-ahead bits of
-// the stream below it, so a renormalisation is two shifts; `look` is the next 16 stream bits, fetched
-// one refill ahead so that the load latency is off the per-bin dependency chain.  Bits past the end
-// of the substream read as zero (same convention as the CPU oracle).
+// the stream below it, so a renormalisation is two shifts.  The stream is consumed 16 bits at a time from
+// 2-byte aligned positions (the initial read takes 2 or 3 bytes to get there); the next two halfwords are
+// always already loaded (`look0`, `look1`), so no load sits on the per-bin dependency chain and the refill
+// path stays a handful of instructions (it is inlined at every bin).  Bits past the end of the substream
+// read as zero (as in the CPU oracle).
 // ------------------------------------------------------------------------------------------------
 struct Engine {
-  const uint8_t* data;
-  uint32_t pos, end;
-  uint32_t range, val, look;
+  const uint8_t* data;   // 2-byte aligned on the device
+  uint32_t pos, end;     // next halfword to fetch (even byte offset from data), substream end
+  uint32_t look0, look1; // prefetched halfwords (big-endian values)
+  uint32_t range, val;
   int nbits;
   uint32_t bins;
 
   HEIC_HD uint32_t byte_at(uint32_t p) const { return p < end ? data[p] : 0u; }
-  HEIC_HD void fetch() {
-    look = (byte_at(pos) << 8) | byte_at(pos + 1);
-    pos += 2;
+  HEIC_HD uint32_t load16(uint32_t p) const {  // p even
+    if (p >= end) return 0u;
+#if defined(__CUDA_ARCH__)
+    uint32_t h = *reinterpret_cast<const uint16_t*>(data + p);
+    h = __byte_perm(h, 0u, 0x4401);
+#else
+    uint32_t h = ((uint32_t)data[p] << 8) | (p + 1 < end ? data[p + 1] : 0u);
+#endif
+    if (p + 1u >= end) h &= 0xff00u;
+    return h;
   }
   // 9.3.2.5 (arithmetic.rs:23-38): ivlCurrRange = 510, ivlOffset = read_bits(9)
   HEIC_HD void init(const uint8_t* d, uint32_t start, uint32_t stop) {
     data = d;
     end = stop;
     range = 510;
-    val = ((byte_at(start) << 16) | (byte_at(start + 1) << 8) | byte_at(start + 2)) << 7;
-    nbits = 15;
-    pos = start + 3;
-    fetch();
+    if (start & 1u) {
+      val = ((byte_at(start) << 16) | (byte_at(start + 1) << 8) | byte_at(start + 2)) << 7;
+      nbits = 15;
+      pos = start + 3;
+    } else {
+      val = ((byte_at(start) << 8) | byte_at(start + 1)) << 15;
+      nbits = 7;
+      pos = start + 2;
+    }
+    look0 = load16(pos);
+    look1 = load16(pos + 2);
+    pos += 4;
   }
   HEIC_HD bool offset_is_illegal() const { return (val >> 22) >= 510u; }
   HEIC_HD void refill() {
     if (nbits < 7) {
-      val |= look << (6 - nbits);
+      val |= look0 << (6 - nbits);
       nbits += 16;
-      fetch();
+      look0 = look1;
+      look1 = load16(pos);
+      pos += 2;
     }
   }
-  // 9.3.4.3.2 (arithmetic.rs:97-135)
-  HEIC_HD int decision(const CabacTabs* T, uint8_t* ctx) {
-    uint32_t s = *ctx;
-    uint32_t lps4 = T->st_lps[s], nx = T->st_next[s];
-    uint32_t q = (range >> 6) & 3u;
-    uint32_t lps = (lps4 >> (q << 3)) & 0xffu;
+  // 9.3.4.3.2 (arithmetic.rs:97-135) on a context state s = pStateIdx << 1 | valMps; returns the bin and
+  // the updated state through s.
+  HEIC_HD int decision(const CabacTabs* T, uint32_t& s) {
+    const uint32_t lps4 = T->st_lps[s];
+    uint32_t nx = T->st_next[s];
+    const uint32_t q = (range >> 6) & 3u;
+    const uint32_t lps = (lps4 >> (q << 3)) & 0xffu;
     range -= lps;
-    uint32_t scaled = range << 22;
+    const uint32_t scaled = range << 22;
     int bin = (int)(s & 1u);
     if (val >= scaled) {
       val -= scaled;
@@ -101,8 +133,8 @@ struct Engine {
       bin ^= 1;
       nx >>= 8;
     }
-    *ctx = (uint8_t)nx;
-    int sh = HEIC_CLZ(range) - 23;  // arithmetic.rs:137-144, all renorm shifts at once
+    s = nx & 0xffu;
+    const int sh = HEIC_CLZ(range) - 23;  // arithmetic.rs:137-144, all renorm shifts at once
     range <<= sh;
     val <<= sh;
     nbits -= sh;
@@ -181,13 +213,28 @@ struct Parser {
   int pu_mode[4];
   int err;
 
-  HEIC_HD int dec(int idx) { return e.decision(T, ctx + idx * STRIDE); }
+#if defined(__CUDA_ARCH__)
+  uint32_t ctx_off;  // byte offset of this thread's context table in the kernel's dynamic shared memory
+  HEIC_HD const CabacTabs* tabs() const { return reinterpret_cast<const CabacTabs*>(heic_cabac_smem); }
+  HEIC_HD uint32_t ld_ctx(int idx) const { return heic_cabac_smem[ctx_off + idx * STRIDE]; }
+  HEIC_HD void st_ctx(int idx, uint32_t v) { heic_cabac_smem[ctx_off + idx * STRIDE] = (uint8_t)v; }
+#else
+  HEIC_HD const CabacTabs* tabs() const { return T; }
+  HEIC_HD uint32_t ld_ctx(int idx) const { return ctx[idx * STRIDE]; }
+  HEIC_HD void st_ctx(int idx, uint32_t v) { ctx[idx * STRIDE] = (uint8_t)v; }
+#endif
+  HEIC_HD int dec(int idx) {
+    uint32_t s = ld_ctx(idx);
+    const int bin = e.decision(tabs(), s);
+    st_ctx(idx, s);
+    return bin;
+  }
   HEIC_HD void fail(int code) {
     if (!err) err = code;
   }
 
   HEIC_HD void init_contexts(int slice_qp) {
-    for (int i = 0; i < NUM_CTX; i++) ctx[i * STRIDE] = context_init_state(T->init_value[i], slice_qp);
+    for (int i = 0; i < NUM_CTX; i++) st_ctx(i, context_init_state(tabs()->init_value[i], slice_qp));
   }
 
   HEIC_HD uint32_t egk_bypass(int k) {  // decoder.rs:206-222 with 32-bit arithmetic
@@ -272,14 +319,14 @@ struct Parser {
     if (scan_idx == 0) {
       uint32_t v;
       if (lg == 2) {
-        v = T->diag4[i];
+        v = tabs()->diag4[i];
         return (v & 3u) | ((v >> 2) << 4);
       }
       if (lg == 3) {
-        v = T->diag8[i];
+        v = tabs()->diag8[i];
         return (v & 7u) | ((v >> 3) << 4);
       }
-      v = T->diag2[i];
+      v = tabs()->diag2[i];
       return (v & 1u) | ((v >> 1) << 4);
     }
     uint32_t a = (uint32_t)i & ((1u << lg) - 1u), b = (uint32_t)i >> lg;
@@ -288,9 +335,9 @@ struct Parser {
   HEIC_HD int scan_inv(int scan_idx, int lg, int x, int y) const {
     if (lg == 0) return 0;
     if (scan_idx == 0) {
-      if (lg == 2) return T->inv_diag4[(y << 2) | x];
-      if (lg == 3) return T->inv_diag8[(y << 3) | x];
-      return T->inv_diag2[(y << 1) | x];
+      if (lg == 2) return tabs()->inv_diag4[(y << 2) | x];
+      if (lg == 3) return tabs()->inv_diag8[(y << 3) | x];
+      return tabs()->inv_diag2[(y << 1) | x];
     }
     return scan_idx == 1 ? ((y << lg) | x) : ((x << lg) | y);
   }
@@ -314,15 +361,19 @@ struct Parser {
     const int n = 1 << log2;
     int tskip = 0;
     if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
-    int last_x = last_sig_coeff_prefix(CTX_LAST_X, c_idx, log2);
-    int last_y = last_sig_coeff_prefix(CTX_LAST_Y, c_idx, log2);
-    if (last_x > 3) {
-      int nb = (last_x >> 1) - 1;
-      last_x = (1 << nb) * (2 + (last_x & 1)) + (int)e.fl_bypass(nb);
-    }
-    if (last_y > 3) {
-      int nb = (last_y >> 1) - 1;
-      last_y = (1 << nb) * (2 + (last_y & 1)) + (int)e.fl_bypass(nb);
+    int last_x, last_y;
+    {
+      int pre[2];
+HEIC_NO_UNROLL
+      for (int d = 0; d < 2; d++) pre[d] = last_sig_coeff_prefix(d ? CTX_LAST_Y : CTX_LAST_X, c_idx, log2);
+HEIC_NO_UNROLL
+      for (int d = 0; d < 2; d++)  // suffixes follow both prefixes (7.3.8.11)
+        if (pre[d] > 3) {
+          const int nb = (pre[d] >> 1) - 1;
+          pre[d] = (1 << nb) * (2 + (pre[d] & 1)) + (int)e.fl_bypass(nb);
+        }
+      last_x = pre[0];
+      last_y = pre[1];
     }
     int scan_idx = 0;
     if (log2 == 2 || (log2 == 3 && c_idx == 0)) {
@@ -368,9 +419,9 @@ struct Parser {
             uint32_t pxy = scan_xy(scan_idx, 2, k);
             int xp = (int)(pxy & 15u), yp = (int)(pxy >> 4);
             int sig_ctx;
-            if (log2 == 2) sig_ctx = T->sig_map4[(yp << 2) + xp];
+            if (log2 == 2) sig_ctx = tabs()->sig_map4[(yp << 2) + xp];
             else if ((xs | ys | xp | yp) == 0) sig_ctx = 0;
-            else sig_ctx = T->sig_pat[prev_csbf][(yp << 2) | xp] + sb_off + sig_off;
+            else sig_ctx = tabs()->sig_pat[prev_csbf][(yp << 2) | xp] + sb_off + sig_off;
             if (dec(sig_base + sig_ctx)) {
               sig |= 1u << k;
               infer_sb_dc = 0;
@@ -485,13 +536,17 @@ struct Parser {
     if (err) return;
     const int ctb4 = 1 << (pp->log2_ctb - 2);
     const uint32_t ti = ctb_addr * (uint32_t)(ctb4 * ctb4) + z4;
-    int ts0 = 0, ts1 = 0, ts2 = 0;
-    if (cbf_luma) ts0 = residual_coding(log2, 0, luma_mode, coeff[0] + (size_t)ti * 16);
-    if (cbf_cb | cbf_cr) {
-      const size_t off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
-      if (cbf_cb) ts1 = residual_coding(log2c, 1, chroma_mode, coeff[1] + off_c);
-      if (cbf_cr) ts2 = residual_coding(log2c, 2, chroma_mode, coeff[2] + off_c);
+    // one residual_coding call site for the three components keeps the kernel's instruction footprint small
+    const size_t off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
+    uint32_t ts = 0;
+HEIC_NO_UNROLL
+    for (int c = 0; c < 3; c++) {
+      const int cbf = c == 0 ? cbf_luma : (c == 1 ? cbf_cb : cbf_cr);
+      if (!cbf) continue;
+      int16_t* dst = c == 0 ? coeff[0] + (size_t)ti * 16 : (c == 1 ? coeff[1] : coeff[2]) + off_c;
+      ts |= (uint32_t)residual_coding(c ? log2c : log2, c, c ? chroma_mode : luma_mode, dst) << c;
     }
+    const int ts0 = (int)(ts & 1u), ts1 = (int)((ts >> 1) & 1u), ts2 = (int)((ts >> 2) & 1u);
     tu_map[ti] = 1u | ((uint32_t)(log2 - 2) << 1) | ((uint32_t)cbf_luma << 3) | ((uint32_t)cbf_cb << 4) |
                  ((uint32_t)cbf_cr << 5) | ((uint32_t)has_chroma << 6) | ((uint32_t)luma_mode << 7) |
                  ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |

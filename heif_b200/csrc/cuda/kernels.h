@@ -17,10 +17,11 @@ cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t*
                          int tiles_per_cta, int n_slots, cudaStream_t stream);
 
 // Stage 2 — scaling (8.6.4.2) + inverse DST/DCT (8.6.4.2), in place on the coefficient arena.
-cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, cudaStream_t stream);
+cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, cudaStream_t stream);
+int transform_launches(int max_log2_tb);
 
 // Stage 3 — intra prediction + reconstruction (8.4.4.2), CTU wavefront per picture.
-cudaError_t launch_intra(const Arenas& A, int max_log2_ctb, int n_slots, cudaStream_t stream);
+cudaError_t launch_intra(const Arenas& A, int max_log2_ctb, int max_hctb, int n_slots, cudaStream_t stream);
 
 // Stage 4 — deblocking (8.7.2), in place on the reconstruction arena.
 cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream);

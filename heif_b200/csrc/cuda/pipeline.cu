@@ -88,6 +88,8 @@ struct heic_b200_ctx {
   uint64_t launches = 0;
   int cabac_tiles_per_cta = 32;  // 32: thread per substream, 1: warp per substream
   int cabac_slots = 0;           // 0: derive from the picture geometry
+  int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
+  int intra_single_warp_tiles = 2048;
   std::unique_ptr<heic_b200_batch> scratch;
   ~heic_b200_ctx();
 };
@@ -115,7 +117,7 @@ struct heic_b200_batch {
   size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0;
   size_t rgb_pitch = 0, rgb_image_stride = 0;
   uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
-  int max_log2_ctb = 4, intra_slots = 1;
+  int max_log2_ctb = 4, max_log2_tb = 2, intra_slots = 1, max_hctb = 1;
   uint32_t stages_run = 0;
   PinnedBuf h_bitstream, h_status;
   DevBuf d_bitstream, d_substreams, d_order, d_pics, d_tiles, d_scaling, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
@@ -161,7 +163,9 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = 0;
   max_tu = max_w = max_h = max_pitch = 0;
   max_log2_ctb = 4;
+  max_log2_tb = 2;
   intra_slots = 1;
+  max_hctb = 1;
   stages_run = 0;
   size_t max_rgb_bytes = 0, max_rgb_pitch = 0;
   for (uint32_t i = 0; i < n_imgs; i++) {
@@ -238,6 +242,8 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     max_h = std::max(max_h, (uint32_t)pp.h);
     max_pitch = std::max(max_pitch, (uint32_t)pp.pitch_y);
     max_log2_ctb = std::max(max_log2_ctb, pp.log2_ctb);
+    max_log2_tb = std::max(max_log2_tb, pp.log2_max_tb);
+    max_hctb = std::max(max_hctb, pp.hctb);
     intra_slots = std::max(intra_slots, std::min(8, std::min(pp.hctb, (pp.wctb + 1) / 2 + 1)));
   }
   rgb_pitch = max_rgb_pitch;
@@ -322,11 +328,14 @@ void heic_b200_batch::run(uint32_t mask) {
     }
   }
   if (mask & HEIC_STAGE_TRANSFORM) {
-    CU(launch_transform(A, max_tu, st));
-    ctx->launches++;
+    CU(launch_transform(A, max_tu, max_log2_tb, st));
+    ctx->launches += transform_launches(max_log2_tb);
   }
   if (mask & HEIC_STAGE_INTRA) {
-    CU(launch_intra(A, max_log2_ctb, intra_slots, st));
+    // enough pictures to fill the GPU with one warp each: drop the intra-picture wavefront (no waiting at all)
+    int slots = tiles.size() >= (size_t)ctx->intra_single_warp_tiles ? 1 : intra_slots;
+    if (ctx->intra_slots > 0) slots = std::min(ctx->intra_slots, std::max(1, max_hctb));
+    CU(launch_intra(A, max_log2_ctb, max_hctb, slots, st));
     ctx->launches++;
   }
   if (mask & HEIC_STAGE_DEBLOCK) {
@@ -426,6 +435,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     CU(cudaMemcpy(c->d_tabs, &tabs, sizeof tabs, cudaMemcpyHostToDevice));
     c->cabac_tiles_per_cta = env_int("HEIC_B200_CABAC_TILES_PER_CTA", 32) == 1 ? 1 : 32;
     c->cabac_slots = env_int("HEIC_B200_CABAC_SLOTS", 0);
+    c->intra_slots = std::min(8, env_int("HEIC_B200_INTRA_SLOTS", 0));
     *out_ctx = c.release();
     return 0;
   }));

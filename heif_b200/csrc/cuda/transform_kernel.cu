@@ -1,12 +1,15 @@
 // Stage 2: scaling (H.265 8.6.4.2 with the 7.4.5 scaling factors) + inverse DST-4 / DCT-4..32 (8.6.4.2),
 // in place on the coefficient arena.  The reference has none of this (slice.rs:253-255 is todo!()).
 //
-// Small integer butterflies, HBM-bound: one warp owns 64 consecutive tu_map entries (a 32x32 luma area,
-// 2 KB of coefficients, plus its two 16x16 chroma areas).  For every transform size the warp sweeps the
-// aligned slots of that size, 32/n transform blocks at a time: a lane runs one n-point 1-D transform per
-// pass (columns, then rows) as an even/odd partial butterfly entirely in registers; the two passes are
-// joined through a padded (conflict-free) shared-memory tile.  Only coded blocks (cbf = 1) are read or
-// written, so DRAM traffic is 2 B in + 2 B out per coded sample.
+// Small integer butterflies, HBM-bound.  One launch per (component kind, transform size) so that every CTA of
+// a launch runs the same straight-line butterfly and the instruction cache holds it (a single kernel with all
+// sizes was instruction-fetch bound).  A warp owns 64 consecutive tu_map entries (a 32x32 luma area and its
+// two 16x16 chroma areas) and sweeps the aligned slots of the launch's size:
+//   n >= 8: 32/n transform blocks at a time; a lane runs one n-point 1-D transform per pass (columns, then
+//           rows) as an even/odd partial butterfly in registers; the passes are joined through a padded
+//           (conflict-free) shared-memory tile and the residual goes back to HBM in lane-contiguous words;
+//   n == 4: one lane per block, both passes in registers, 32 blocks per warp step, 32-byte loads/stores.
+// Only coded blocks (cbf = 1) are read or written, so DRAM traffic is 2 B in + 2 B out per coded sample.
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -90,7 +93,8 @@ struct WarpCtx {
   const TileParams* tp;
   const ScalingSet* sc;
   int16_t* tmp;   // this warp's padded transpose tile
-  uint32_t w0, w1;  // tu_map words of entries lane and lane + 32 of the region
+  const uint32_t* tu;  // the region's 64 tu_map words
+  int n_entries;       // valid entries of the region (< 64 only at the end of a CTB-16 picture)
   int lane;
 };
 
@@ -111,27 +115,12 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
     bool active = false;
     uint32_t w;
     {
-      // shuffles are warp-collective: lanes without a slot of this size fetch slot 0 and discard it
-      const bool has_slot = slot < SLOTS;
+      const bool has_slot = slot < SLOTS && slot * EPB < c.n_entries;
       const int entry = has_slot ? slot * EPB : 0;
-      const uint32_t a = __shfl_sync(0xffffffffu, c.w0, entry & 31), b = __shfl_sync(0xffffffffu, c.w1, entry & 31);
-      const uint32_t a3 = __shfl_sync(0xffffffffu, c.w0, (entry + 3) & 31), b3 = __shfl_sync(0xffffffffu, c.w1, (entry + 3) & 31);
-      w = entry < 32 ? a : b;
-      const uint32_t w3 = entry < 32 ? a3 : b3;
+      w = c.tu[entry];  // lanes of one block read the same word (broadcast)
       const uint32_t cbf_bit = CIDX == 0 ? TU_CBF_Y : (CIDX == 1 ? TU_CBF_CB : TU_CBF_CR);
-      if (CIDX == 0) {
-        active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 && (w & cbf_bit);
-      } else if (N > 4) {
-        active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 + 1 && (w & cbf_bit);
-      } else {
-        // 4x4 chroma: luma TU 8x8 at this entry, or the fourth 4x4 luma TU of a split 8x8 (entry + 3)
-        if ((w & TU_ORIGIN) && tu_log2(w) == 3) {
-          active = (w & cbf_bit) != 0;
-        } else if ((w & TU_ORIGIN) && tu_log2(w) == 2 && (w3 & TU_ORIGIN) && (w3 & TU_HAS_CHROMA)) {
-          w = w3;
-          active = (w & cbf_bit) != 0;
-        }
-      }
+      if (CIDX == 0) active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 && (w & cbf_bit);
+      else active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 + 1 && (w & cbf_bit);
       active = active && has_slot;
     }
     if (!__any_sync(0xffffffffu, active)) continue;
@@ -157,16 +146,12 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
       constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
 #pragma unroll
       for (int j = 0; j < N; j++) {
-        int lvl = blk[j * N + col];
-        int v = 0;
-        if (lvl) {
-          int mm = m ? (int)m[j * N + col] : 16;
-          long long p = (long long)lvl * (mm * scale) + (1ll << (BD_SHIFT - 1));
-          p >>= BD_SHIFT;
-          v = (int)(p < -32768 ? -32768 : (p > 32767 ? 32767 : p));
-          nz_rows = j + 1;
-        }
-        x[j] = v;
+        const int lvl = blk[j * N + col];
+        const int mm = m ? (int)m[j * N + col] : 16;
+        long long p = (long long)lvl * (mm * scale) + (1ll << (BD_SHIFT - 1));
+        p >>= BD_SHIFT;
+        x[j] = (int)min(32767ll, max(-32768ll, p));
+        nz_rows = lvl ? j + 1 : nz_rows;
       }
     } else {
 #pragma unroll
@@ -245,6 +230,9 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
 constexpr int kWarpsPerCta = 8;
 constexpr int kTmpPerWarp = 32 * 34;  // int16 elements: one 32x32 block with padded rows
 
+// ---- n >= 8: one launch per (CIDX kind, N) ------------------------------------------------------------------
+// KIND 0: luma, KIND 1: chroma (Cb then Cr)
+template <int N, int KIND>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A) {
   __shared__ __align__(16) int16_t tmp_all[kWarpsPerCta][kTmpPerWarp];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -252,73 +240,146 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A) 
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0) return;
+  if (KIND == 1 && !pp->chroma) return;
   const uint32_t region = blockIdx.y * kWarpsPerCta + warp;
-  const uint32_t n_regions = ((uint32_t)pp->n_tu + 63u) / 64u;
-  if (region >= n_regions) return;
-  const uint32_t* tu = A.tu_map + tp->tu_off + (size_t)region * 64;
+  if (region * 64 >= (uint32_t)pp->n_tu) return;
   WarpCtx c;
   c.pp = pp;
   c.tp = tp;
   c.sc = A.scaling + pp->scaling_set;
   c.tmp = tmp_all[warp];
   c.lane = lane;
-  const uint32_t n_tu = (uint32_t)pp->n_tu;
-  c.w0 = region * 64 + lane < n_tu ? tu[lane] : 0u;
-  c.w1 = region * 64 + 32 + lane < n_tu ? tu[32 + lane] : 0u;
-  const uint32_t any_y = __ballot_sync(0xffffffffu, ((c.w0 | c.w1) & TU_CBF_Y) != 0);
-  const uint32_t any_c = __ballot_sync(0xffffffffu, ((c.w0 | c.w1) & (TU_CBF_CB | TU_CBF_CR)) != 0);
-  if (any_y) {
-    int16_t* y = A.coeff + tp->coeff_off[0] + (size_t)region * 1024;
-    uint32_t sizes = 0;  // bit l set: some coded luma block of log2 size l + 2 exists in the region
-    {
-      uint32_t s = 0;
-      if (c.w0 & TU_CBF_Y) s |= 1u << ((c.w0 >> 1) & 3);
-      if (c.w1 & TU_CBF_Y) s |= 1u << ((c.w1 >> 1) & 3);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) s |= __shfl_xor_sync(0xffffffffu, s, o);
-      sizes = s;
-    }
-    if (sizes & 8u) run_size<32, 0>(c, y);
-    if (sizes & 4u) run_size<16, 0>(c, y);
-    if (sizes & 2u) run_size<8, 0>(c, y);
-    if (sizes & 1u) run_size<4, 0>(c, y);
+  c.tu = A.tu_map + tp->tu_off + (size_t)region * 64;
+  c.n_entries = min(64, pp->n_tu - (int)region * 64);
+  if (KIND == 0) {
+    run_size<N, 0>(c, A.coeff + tp->coeff_off[0] + (size_t)region * 1024);
+  } else {
+    run_size<N, 1>(c, A.coeff + tp->coeff_off[1] + (size_t)region * 256);
+    run_size<N, 2>(c, A.coeff + tp->coeff_off[2] + (size_t)region * 256);
   }
-  if (any_c && pp->chroma) {
-    int16_t* cb = A.coeff + tp->coeff_off[1] + (size_t)region * 256;
-    int16_t* cr = A.coeff + tp->coeff_off[2] + (size_t)region * 256;
-    uint32_t sizes = 0;  // by chroma log2 size - 2
-    {
-      uint32_t s = 0;
-      if (c.w0 & (TU_CBF_CB | TU_CBF_CR)) s |= 1u << max(0, (int)((c.w0 >> 1) & 3) - 1);
-      if (c.w1 & (TU_CBF_CB | TU_CBF_CR)) s |= 1u << max(0, (int)((c.w1 >> 1) & 3) - 1);
+}
+
+// ---- n == 4: one lane per block -----------------------------------------------------------------------------
+__device__ __forceinline__ void idct4(const int (&x)[4], int (&y)[4]) {
+  const int e0 = 64 * (x[0] + x[2]), e1 = 64 * (x[0] - x[2]);
+  const int o0 = 83 * x[1] + 36 * x[3], o1 = 36 * x[1] - 83 * x[3];
+  y[0] = e0 + o0;
+  y[1] = e1 + o1;
+  y[2] = e1 - o1;
+  y[3] = e0 - o0;
+}
+
+template <int CIDX>
+__device__ __forceinline__ void block4(int16_t* blk, uint32_t w, const PicParams* pp, const TileParams* tp, const ScalingSet* sc) {
+  const uint4 in0 = reinterpret_cast<const uint4*>(blk)[0], in1 = reinterpret_cast<const uint4*>(blk)[1];
+  const uint32_t raw[8] = {in0.x, in0.y, in0.z, in0.w, in1.x, in1.y, in1.z, in1.w};
+  int qp = (int)tu_qp(w);
+  if (CIDX) {
+    int qpi = qp + (CIDX == 1 ? pp->pps_cb_qp_offset + tp->slice_cb_qp_offset : pp->pps_cr_qp_offset + tp->slice_cr_qp_offset);
+    qpi = min(57, max(0, qpi));
+    qp = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
+  }
+  const int scale = (int)kLevelScale[qp % 6] << (qp / 6);
+  uint32_t mraw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
+  if (pp->scaling_enabled) {
+    const uint4 mv = *reinterpret_cast<const uint4*>(sc->f4[CIDX]);
+    mraw[0] = mv.x, mraw[1] = mv.y, mraw[2] = mv.z, mraw[3] = mv.w;
+  }
+  int d[16];
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s |= __shfl_xor_sync(0xffffffffu, s, o);
-      sizes = s;
+  for (int i = 0; i < 16; i++) {
+    const int lvl = (int)(int16_t)((raw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+    const int mm = (int)((mraw[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    long long p = (long long)lvl * (mm * scale) + 16;  // bdShift = 5 for 4x4, 8-bit
+    p >>= 5;
+    d[i] = (int)min(32767ll, max(-32768ll, p));
+  }
+  int out[16];
+  if (tu_tskip(w, CIDX)) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) out[i] = ((d[i] << 7) + 2048) >> 12;
+  } else {
+    int t[16];
+#pragma unroll
+    for (int cc = 0; cc < 4; cc++) {  // columns
+      const int x[4] = {d[cc], d[4 + cc], d[8 + cc], d[12 + cc]};
+      int y[4];
+      if (CIDX == 0) dst4(x, y);
+      else idct4(x, y);
+#pragma unroll
+      for (int i = 0; i < 4; i++) t[i * 4 + cc] = clip16((y[i] + 64) >> 7);
     }
-    if (sizes & 4u) {
-      run_size<16, 1>(c, cb);
-      run_size<16, 2>(c, cr);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {  // rows
+      const int x[4] = {t[r * 4], t[r * 4 + 1], t[r * 4 + 2], t[r * 4 + 3]};
+      int y[4];
+      if (CIDX == 0) dst4(x, y);
+      else idct4(x, y);
+#pragma unroll
+      for (int i = 0; i < 4; i++) out[r * 4 + i] = clip16((y[i] + 2048) >> 12);
     }
-    if (sizes & 2u) {
-      run_size<8, 1>(c, cb);
-      run_size<8, 2>(c, cr);
+  }
+  uint32_t pk[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) pk[i] = ((uint32_t)out[2 * i] & 0xffffu) | ((uint32_t)out[2 * i + 1] << 16);
+  reinterpret_cast<uint4*>(blk)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  reinterpret_cast<uint4*>(blk)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// KIND 0: luma 4x4 TUs (a thread per tu_map entry); KIND 1: chroma 4x4 (a thread per 8x8 luma area and component)
+template <int KIND>
+__global__ void __launch_bounds__(256) transform4_kernel(Arenas A) {
+  const uint32_t tile = blockIdx.x;
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+  if (A.status[tile].code != 0) return;
+  const ScalingSet* sc = A.scaling + pp->scaling_set;
+  const uint32_t* tu = A.tu_map + tp->tu_off;
+  const uint32_t i = blockIdx.y * blockDim.x + threadIdx.x;
+  if (KIND == 0) {
+    if (i >= (uint32_t)pp->n_tu) return;
+    const uint32_t w = tu[i];
+    if ((w & TU_ORIGIN) && tu_log2(w) == 2 && (w & TU_CBF_Y)) block4<0>(A.coeff + tp->coeff_off[0] + (size_t)i * 16, w, pp, tp, sc);
+  } else {
+    if (!pp->chroma) return;
+    const uint32_t slot = i >> 1, comp = i & 1;  // Cb / Cr of one slot on adjacent lanes
+    if (slot * 4 >= (uint32_t)pp->n_tu) return;
+    uint32_t w = tu[slot * 4];
+    bool ok = false;
+    if ((w & TU_ORIGIN) && tu_log2(w) == 3) ok = true;             // 8x8 luma TU -> 4x4 chroma
+    else if ((w & TU_ORIGIN) && tu_log2(w) == 2) {                  // split 8x8: chroma rides on blkIdx 3
+      w = tu[slot * 4 + 3];
+      ok = (w & TU_ORIGIN) && (w & TU_HAS_CHROMA);
     }
-    if (sizes & 1u) {
-      run_size<4, 1>(c, cb);
-      run_size<4, 2>(c, cr);
+    if (!ok) return;
+    if (comp == 0) {
+      if (w & TU_CBF_CB) block4<1>(A.coeff + tp->coeff_off[1] + (size_t)slot * 16, w, pp, tp, sc);
+    } else {
+      if (w & TU_CBF_CR) block4<2>(A.coeff + tp->coeff_off[2] + (size_t)slot * 16, w, pp, tp, sc);
     }
   }
 }
 
 }  // namespace
 
-cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, cudaStream_t stream) {
+cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
   const uint32_t regions = (max_tu_per_tile + 63u) / 64u;
-  dim3 grid(A.n_tiles, (regions + kWarpsPerCta - 1) / kWarpsPerCta);
-  transform_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(A);
+  const dim3 grid(A.n_tiles, (regions + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
+  if (max_log2_tb >= 5) {
+    transform_kernel<32, 0><<<grid, block, 0, stream>>>(A);
+    transform_kernel<16, 1><<<grid, block, 0, stream>>>(A);
+  }
+  if (max_log2_tb >= 4) {
+    transform_kernel<16, 0><<<grid, block, 0, stream>>>(A);
+    transform_kernel<8, 1><<<grid, block, 0, stream>>>(A);
+  }
+  transform_kernel<8, 0><<<grid, block, 0, stream>>>(A);
+  transform4_kernel<0><<<dim3(A.n_tiles, (max_tu_per_tile + 255) / 256), 256, 0, stream>>>(A);
+  transform4_kernel<1><<<dim3(A.n_tiles, (max_tu_per_tile / 2 + 255) / 256), 256, 0, stream>>>(A);
   return cudaGetLastError();
 }
+int transform_launches(int max_log2_tb) { return 3 + (max_log2_tb >= 4 ? 2 : 0) + (max_log2_tb >= 5 ? 2 : 0); }
 
 }  // namespace dev
 }  // namespace heic

@@ -67,7 +67,7 @@ extern "C" int emul_parse_picture(const heic_sps* sps, const heic_pps* pps, cons
       P.ct_depth = ctd.data();
       P.qp_map = qp.data();
       P.sao = sao;
-      P.e.data = rbsp;
+      P.e.data = rbsp;  // the host build of Engine::load_word reads byte-wise and never past `end`
       *ctus += parse_rows<1>(P, sh->substream_offset, slot, n_slots, sync);
       *bins += P.e.bins;
       err = P.err;
