@@ -88,6 +88,8 @@ struct heic_b200_ctx {
   uint64_t launches = 0;
   int cabac_tiles_per_cta = 32;  // 32: thread per substream, 1: warp per substream
   int cabac_slots = 0;           // 0: derive from the picture geometry
+  int cabac_group_factor = 1;    // CABAC CTAs per 32 tiles; > 1 splits heavy groups (measured slower: a CTA costs its
+                                 // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
   std::unique_ptr<heic_b200_batch> scratch;
@@ -266,12 +268,33 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     if (ctx->cabac_slots > 0 && wpp) c.n_slots = std::min(hctb, ctx->cabac_slots);
     c.n_slots = std::min(c.n_slots, tpc == 32 ? 8 : 16);
     c.order_off = (uint32_t)order.size();
-    c.n_groups = (uint32_t)((v.size() + tpc - 1) / tpc);
-    for (uint32_t g = 0; g < c.n_groups; g++)
-      for (int l = 0; l < tpc; l++) {
-        size_t idx = (size_t)g * tpc + l;
-        order.push_back(idx < v.size() ? v[idx] : 0xffffffffu);
+    // Tiles stay sorted by slice size so that the lanes of a warp carry similar statistics: measured on a B200,
+    // dealing heavy and light tiles round-robin into the same warp is 3.5x slower (the light lanes idle while one
+    // heavy lane runs at single-thread latency).  With group_factor > 1 the sorted list is additionally cut into
+    // groups of about equal slice bytes (heavy groups get fewer lanes); that measured slower too, see DESIGN.md.
+    c.n_groups = 0;
+    if (tpc == 1) {
+      for (uint32_t t : v) order.push_back(t);
+      c.n_groups = (uint32_t)v.size();
+    } else {
+      uint64_t total = 0;
+      for (uint32_t t : v) total += tiles[t].bs_len;
+      const uint64_t target_groups = std::max<uint64_t>(1, (uint64_t)ctx->cabac_group_factor * ((v.size() + tpc - 1) / tpc));
+      const uint64_t w_target = std::max<uint64_t>(1, total / target_groups);
+      size_t i = 0;
+      while (i < v.size()) {
+        uint64_t wsum = 0;
+        int n = 0;
+        while (i < v.size() && n < tpc && (n == 0 || wsum + tiles[v[i]].bs_len <= w_target)) {
+          wsum += tiles[v[i]].bs_len;
+          order.push_back(v[i]);
+          i++;
+          n++;
+        }
+        for (; n < tpc; n++) order.push_back(0xffffffffu);
+        c.n_groups++;
       }
+    }
     classes.push_back(c);
   }
 
@@ -436,6 +459,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_tiles_per_cta = env_int("HEIC_B200_CABAC_TILES_PER_CTA", 32) == 1 ? 1 : 32;
     c->cabac_slots = env_int("HEIC_B200_CABAC_SLOTS", 0);
     c->intra_slots = std::min(8, env_int("HEIC_B200_INTRA_SLOTS", 0));
+    c->cabac_group_factor = std::max(1, env_int("HEIC_B200_CABAC_GROUP_FACTOR", 1));
     *out_ctx = c.release();
     return 0;
   }));
