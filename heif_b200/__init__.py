@@ -20,7 +20,7 @@ from ._capi import HeicError, STAGE_ALL, STAGE_CABAC, STAGE_COLOR, STAGE_DEBLOCK
 
 __all__ = [
     "HeicDecoder", "HeicFile", "HeifReader", "Batch", "HeicError", "remove_emulation_prevention", "parse_sps", "parse_pps",
-    "parse_slice_header", "STAGE_ALL", "STAGE_CABAC", "STAGE_TRANSFORM", "STAGE_INTRA", "STAGE_DEBLOCK", "STAGE_SAO",
+    "parse_slice_header", "read_ue", "read_se", "STAGE_ALL", "STAGE_CABAC", "STAGE_TRANSFORM", "STAGE_INTRA", "STAGE_DEBLOCK", "STAGE_SAO",
     "STAGE_COLOR",
 ]
 
@@ -42,6 +42,20 @@ def remove_emulation_prevention(data: bytes, with_positions: bool = False):
     if with_positions:
         return res, [int(pos[i]) for i in range(n_epb.value)]
     return res
+
+
+def read_ue(data: bytes, bit_pos: int = 0):
+    """RbspReader::read_ue (rbsp_reader.rs:87) -> (value, new bit position)."""
+    pos, out = C.c_size_t(bit_pos), K.u32()
+    K.check(_lib().heic_b200_rbsp_read_ue(bytes(data), len(data), C.byref(pos), C.byref(out)))
+    return out.value, pos.value
+
+
+def read_se(data: bytes, bit_pos: int = 0):
+    """RbspReader::read_se (rbsp_reader.rs:101) -> (value, new bit position)."""
+    pos, out = C.c_size_t(bit_pos), K.i32()
+    K.check(_lib().heic_b200_rbsp_read_se(bytes(data), len(data), C.byref(pos), C.byref(out)))
+    return out.value, pos.value
 
 
 def parse_sps(rbsp: bytes) -> K.Sps:

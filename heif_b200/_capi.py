@@ -142,6 +142,8 @@ SYMBOLS = [
     ("heic_b200_launch_count", C.c_uint64, [_vp]),
     ("heic_b200_remove_emulation_prevention", C.c_int64,
      [C.c_char_p, _sz, C.POINTER(u8), C.POINTER(u32), _sz, C.POINTER(_sz)]),
+    ("heic_b200_rbsp_read_ue", i32, [C.c_char_p, _sz, C.POINTER(_sz), C.POINTER(u32)]),
+    ("heic_b200_rbsp_read_se", i32, [C.c_char_p, _sz, C.POINTER(_sz), C.POINTER(i32)]),
     ("heic_b200_parse_sps", i32, [C.c_char_p, _sz, C.POINTER(Sps)]),
     ("heic_b200_parse_pps", i32, [C.c_char_p, _sz, C.POINTER(Pps)]),
     ("heic_b200_parse_slice_header", i32,

@@ -35,6 +35,26 @@ int64_t heic_b200_remove_emulation_prevention(const uint8_t* data, size_t len, u
   });
 }
 
+static int64_t read_golomb(const uint8_t* data, size_t len, size_t* bit_pos, bool is_signed, void* out) {
+  return guard([&]() -> int64_t {
+    if (!data || !bit_pos || !out) bail(HEIC_E_INVALID_ARG, "null argument");
+    RbspReader r(data, len);
+    if (*bit_pos > len * 8) bail(HEIC_E_INVALID_ARG, "bit position beyond the buffer");
+    r.read_bits(0);
+    for (size_t i = 0; i < *bit_pos; ++i) r.read_bit();
+    if (is_signed) *static_cast<int32_t*>(out) = r.read_se();
+    else *static_cast<uint32_t*>(out) = r.read_ue();
+    *bit_pos = r.byte_position() * 8 + r.bit_position();
+    return 0;
+  });
+}
+int32_t heic_b200_rbsp_read_ue(const uint8_t* data, size_t len, size_t* bit_pos, uint32_t* out) {
+  return static_cast<int32_t>(read_golomb(data, len, bit_pos, false, out));
+}
+int32_t heic_b200_rbsp_read_se(const uint8_t* data, size_t len, size_t* bit_pos, int32_t* out) {
+  return static_cast<int32_t>(read_golomb(data, len, bit_pos, true, out));
+}
+
 int32_t heic_b200_parse_sps(const uint8_t* rbsp, size_t len, heic_sps* out) {
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!rbsp || !out) bail(HEIC_E_INVALID_ARG, "null argument");

@@ -197,6 +197,10 @@ uint64_t heic_b200_launch_count(const heic_b200_ctx* ctx);
  * to epb_cap positions (in the escaped input) of every removed 0x03 byte; *n_epb gets the count. */
 int64_t heic_b200_remove_emulation_prevention(const uint8_t* data, size_t len, uint8_t* out,
                                               uint32_t* epb_pos, size_t epb_cap, size_t* n_epb);
+/* RbspReader::read_ue / read_se                                  src/hevc/rbsp_reader.rs:87,101
+ * Reads one Exp-Golomb code starting at bit *bit_pos of data (MSB first) and advances *bit_pos. */
+int32_t heic_b200_rbsp_read_ue(const uint8_t* data, size_t len, size_t* bit_pos, uint32_t* out);
+int32_t heic_b200_rbsp_read_se(const uint8_t* data, size_t len, size_t* bit_pos, int32_t* out);
 /* video/sequence/picture_parameter_set_rbsp                     src/hevc/parameter_set_reader.rs:7,36,351
  * Input is the un-escaped RBSP without the 2-byte NAL header. */
 int32_t heic_b200_parse_sps(const uint8_t* rbsp, size_t len, heic_sps* out);

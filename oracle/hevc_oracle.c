@@ -198,6 +198,8 @@ typedef struct {
   uint32_t range, offset;
   uint8_t ctx[NUM_CTX], ctx_wpp[NUM_CTX]; /* pStateIdx<<1 | valMps */
   uint32_t bins;
+  const uint8_t* test_bins; /* unit tests only: bins come from this list instead of the arithmetic decoder */
+  int test_n, test_i;
   /* per-picture maps */
   uint8_t* ct_depth; /* per 8x8 */
   uint8_t* ipm;      /* luma IntraPredModeY per 4x4 */
@@ -302,7 +304,10 @@ static inline void renorm(Dec* d) { /* arithmetic.rs:137-144 */
 }
 
 /* 9.3.4.3.2 (arithmetic.rs:97-135) */
+static int test_bin(Dec* d) { return d->test_i < d->test_n ? d->test_bins[d->test_i++] : 0; }
+
 static int decode_decision(Dec* d, int ctx_idx) {
+  if (d->test_bins) return test_bin(d);
   uint8_t s = d->ctx[ctx_idx];
   uint32_t p = s >> 1, mps = s & 1;
   uint32_t q = (d->range >> 6) & 3;
@@ -327,6 +332,7 @@ static int decode_decision(Dec* d, int ctx_idx) {
 
 /* 9.3.4.3.4 (arithmetic.rs:146-157) */
 static int decode_bypass(Dec* d) {
+  if (d->test_bins) return test_bin(d);
   d->bins++;
   d->offset = (d->offset << 1) | read_bit(d);
   if (d->offset >= d->range) {
@@ -999,6 +1005,12 @@ static int derive_luma_mode(Dec* d, int x, int y, int prev_flag, int mpm_idx, in
   return mode;
 }
 
+/* intra_chroma_pred_mode binarisation, Table 9-41 (decoder.rs:23-35,192-204): "0" -> 4, "1" + FL(2) -> 0..3 */
+static int decode_intra_chroma_pred_mode_idx(Dec* d) {
+  if (!decode_decision(d, CTX_CHROMA_PRED)) return 4;
+  return (int)decode_fl_bypass(d, 2);
+}
+
 /* 7.3.8.5 coding_unit (I slice) */
 static void coding_unit(Dec* d, int x0, int y0, int log2) {
   int n = 1 << log2;
@@ -1037,8 +1049,7 @@ static void coding_unit(Dec* d, int x0, int y0, int log2) {
     }
   d->chroma_mode = 0;
   if (d->chroma) { /* intra_chroma_pred_mode (decoder.rs:23-35,192-204) + 8.4.3 */
-    int idx = 4;
-    if (decode_decision(d, CTX_CHROMA_PRED)) idx = (int)decode_fl_bypass(d, 2);
+    int idx = decode_intra_chroma_pred_mode_idx(d);
     int luma = d->ipm[(y0 >> 2) * d->w4 + (x0 >> 2)];
     static const uint8_t kMap[4] = {0, 26, 10, 1};
     if (idx == 4) d->chroma_mode = luma;
@@ -1397,6 +1408,34 @@ int hevc_oracle_decode_picture(const heic_sps* sps, const heic_pps* pps, const h
 int hevc_oracle_parse_picture(const heic_sps* sps, const heic_pps* pps, const heic_slice_header* sh,
                               const uint8_t* rbsp, uint32_t rbsp_len, hevc_oracle_out* out) {
   return decode_impl(sps, pps, sh, rbsp, rbsp_len, out, 1);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* Unit-test hooks: run one binarisation on a caller-supplied bin string, exactly as the reference's   */
+/* tests feed decode_truncated_rice / decode_intra_chroma_pred_mode_bins from a bin iterator           */
+/* (cabac/decoder.rs:286-374).  kind 0: TR prefix with cRiceParam 0 and cMax = arg (Table 9-39);        */
+/* 1: intra_chroma_pred_mode (Table 9-41); 2: EGk with k = arg; 3: coeff_abs_level_remaining with        */
+/* cRiceParam = arg; 4: FL with arg bits.  Returns the decoded value; *consumed = bins read.             */
+/* ------------------------------------------------------------------------------------------ */
+uint32_t hevc_oracle_test_binarization(int kind, uint32_t arg, const uint8_t* bins, int n_bins, int* consumed) {
+  Dec* d = (Dec*)calloc(1, sizeof(Dec));
+  hevc_oracle_out out;
+  memset(&out, 0, sizeof out);
+  static const uint8_t kNone = 0;
+  d->out = &out;
+  d->test_bins = n_bins ? bins : &kNone;
+  d->test_n = n_bins;
+  uint32_t v = 0;
+  switch (kind) {
+    case 0: v = decode_tr_bypass(d, arg); break;
+    case 1: v = (uint32_t)decode_intra_chroma_pred_mode_idx(d); break;
+    case 2: v = decode_egk_bypass(d, (int)arg); break;
+    case 3: v = decode_coeff_abs_level_remaining(d, (int)arg); break;
+    default: v = decode_fl_bypass(d, (int)arg); break;
+  }
+  if (consumed) *consumed = d->test_i;
+  free(d);
+  return v;
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -48,6 +48,8 @@ void hevc_oracle_color_stitch(const uint8_t* planes, uint32_t grid_rows, uint32_
 void hevc_oracle_idct(const int16_t* coeff, int16_t* resid, int log2_size, int dst);   /* 8.6.4.2, 8-bit */
 void hevc_oracle_context_init(int slice_qp, uint8_t* state /* [HEVC_ORACLE_NUM_CTX] = pStateIdx<<1 | valMps */);
 #define HEVC_ORACLE_NUM_CTX 134
+/* Binarisations on a caller-supplied bin string (the shape of the reference's own tests, cabac/decoder.rs:286-374). */
+uint32_t hevc_oracle_test_binarization(int kind, uint32_t arg, const uint8_t* bins, int n_bins, int* consumed);
 uint32_t hevc_oracle_tu_map_len(const heic_sps* sps);
 uint32_t hevc_oracle_coeff_len(const heic_sps* sps, int c_idx);
 

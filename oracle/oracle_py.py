@@ -47,6 +47,8 @@ def load():
         lib.hevc_oracle_idct.restype = None
         lib.hevc_oracle_context_init.argtypes = [C.c_int, C.c_void_p]
         lib.hevc_oracle_context_init.restype = None
+        lib.hevc_oracle_test_binarization.argtypes = [C.c_int, C.c_uint32, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
+        lib.hevc_oracle_test_binarization.restype = C.c_uint32
         lib.hevc_oracle_tu_map_len.argtypes = [C.POINTER(K.Sps)]
         lib.hevc_oracle_tu_map_len.restype = C.c_uint32
         lib.hevc_oracle_coeff_len.argtypes = [C.POINTER(K.Sps), C.c_int]
@@ -135,3 +137,12 @@ def context_init(slice_qp: int) -> np.ndarray:
     st = np.zeros(134, np.uint8)
     lib.hevc_oracle_context_init(slice_qp, st.ctypes.data)
     return st
+
+
+def test_binarization(kind: int, arg: int, bins) -> tuple[int, int]:
+    """(value, bins consumed) of one binarisation fed from a bin list (kinds: see hevc_oracle.c)."""
+    lib = load()
+    b = bytes(int(bool(x)) for x in bins)
+    used = C.c_int()
+    v = lib.hevc_oracle_test_binarization(kind, arg, b, len(b), C.byref(used))
+    return int(v), used.value

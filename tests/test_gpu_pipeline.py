@@ -1,0 +1,178 @@
+"""GPU parity of the whole path through the reference-facing C ABI (host descriptors in, host pixels out), against the
+committed FFmpeg golden hashes and the CPU oracle.  Bit-exact: every stage is integer."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import heif_b200 as H
+from heif_b200 import _capi as K
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "fixture_hashes.json")))
+
+
+def permuted_image(base, perm):
+    tiles = (K.TileDesc * base.n_tiles)()
+    for d, s in enumerate(perm):
+        C.memmove(C.byref(tiles, d * C.sizeof(K.TileDesc)), C.byref(base.tiles[int(s)]), C.sizeof(K.TileDesc))
+    im = K.ImageDesc()
+    C.memmove(C.byref(im), C.byref(base), C.sizeof(K.ImageDesc))
+    im.tiles = C.cast(tiles, C.POINTER(K.TileDesc))
+    return im, tiles
+
+
+@pytest.fixture(scope="module")
+def oracle_rgb(heic_file, oracle_tiles):
+    img = heic_file.primary
+    planes = np.concatenate([np.concatenate([p.ravel() for p in oracle_tiles(t)["plane"]]) for t in range(img.n_tiles)])
+    return O.color_stitch(planes, img.grid_rows, img.grid_cols, 512, 512, img.output_width, img.output_height,
+                          img.sps.video_full_range_flag, img.sps.matrix_coeffs)
+
+
+def test_yuv_matches_ffmpeg_golden(decoder, heic_file):
+    (y, cb, cr), = decoder.decode_grids_yuv([heic_file.primary])
+    assert y.shape == (3024, 4032) and cb.shape == (1512, 2016)
+    got = [hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in (y, cb, cr)]
+    assert got == GOLDEN["stitched"]
+
+
+def test_decode_file_rgb_matches_oracle(decoder, fixture_bytes, oracle_rgb):
+    rgb = decoder.decode(fixture_bytes)
+    assert rgb.shape == (3024, 4032, 3)
+    assert np.array_equal(rgb, oracle_rgb)
+
+
+@pytest.mark.parametrize("turns", [1, 2, 3])
+def test_irot_rotation(decoder, heic_file, oracle_rgb, turns):
+    img = K.ImageDesc()
+    C.memmove(C.byref(img), C.byref(heic_file.primary), C.sizeof(K.ImageDesc))
+    img.rotation_ccw_quarter_turns = turns
+    rgb = decoder.decode_grids([img], apply_transforms=True)[0]
+    assert np.array_equal(rgb, np.rot90(oracle_rgb, turns))
+
+
+def test_file_rotation_is_the_irot_of_the_fixture(decoder, fixture_bytes, oracle_rgb):
+    rgb = decoder.decode(fixture_bytes, apply_transforms=True)
+    assert rgb.shape == (4032, 3024, 3)  # irot = 3 -> 3024 x 4032 (libheif_comparison.rs:69-74)
+    assert np.array_equal(rgb, np.rot90(oracle_rgb, 3))
+
+
+def test_batch_of_permuted_images_is_the_permutation_of_the_outputs(decoder, heic_file, oracle_rgb):
+    """Size-independent property: tiles are independent pictures, so permuting tiles permutes 512x512 blocks of the output."""
+    base = heic_file.primary
+    rng = np.random.default_rng(7)
+    perms = [rng.permutation(48) for _ in range(5)]
+    imgs, keep = zip(*[permuted_image(base, p) for p in perms])
+    out = decoder.decode_grids(list(imgs))
+    ref_full = np.zeros((3072, 4096, 3), np.uint8)
+    planes = None
+    for k, perm in enumerate(perms):
+        for d, s in enumerate(perm):
+            r, c = divmod(d, 8)
+            rs, cs = divmod(int(s), 8)
+            y0, x0 = r * 512, c * 512
+            h, w = min(512, 3024 - y0), min(512, 4032 - x0)
+            hs, ws = min(512, 3024 - rs * 512), min(512, 4032 - cs * 512)
+            hh, ww = min(h, hs), min(w, ws)
+            assert np.array_equal(out[k, y0:y0 + hh, x0:x0 + ww], oracle_rgb[rs * 512:rs * 512 + hh, cs * 512:cs * 512 + ww]), (k, d)
+
+
+def test_corrupt_tile_is_reported_per_tile_and_does_not_poison_the_batch(decoder, heic_file, oracle_rgb):
+    base = heic_file.primary
+    img, tiles = permuted_image(base, list(range(48)))
+    bad = bytearray(bytes(base.tiles[10].rbsp[: base.tiles[10].rbsp_len]))
+    off = base.tiles[10].header.slice_data_byte_offset
+    for i in range(off + 64, len(bad)):
+        bad[i] = (bad[i] * 29 + 17) & 0xFF
+    buf = (C.c_uint8 * len(bad)).from_buffer(bad)
+    tiles[10].rbsp = C.cast(buf, C.POINTER(K.u8))
+    out, rc, st = decoder.decode_grids([img], return_status=True)
+    assert rc == K.HEIC_E_BITSTREAM
+    assert st[10].code != 0
+    assert all(st[t].code == 0 for t in range(48) if t != 10)
+    # every other tile is still bit-exact
+    for t in range(48):
+        if t == 10:
+            continue
+        r, c = divmod(t, 8)
+        y0, x0 = r * 512, c * 512
+        assert np.array_equal(out[0, y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)],
+                              oracle_rgb[y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)]), t
+    # truncated stream: must terminate (zeros past the end) and be flagged
+    img2, tiles2 = permuted_image(base, list(range(48)))
+    tiles2[0].rbsp_len = base.tiles[0].header.slice_data_byte_offset + 20
+    # keep the entry points inside the (now short) RBSP so the host accepts the descriptor
+    for k in range(1, 16):
+        tiles2[0].header.substream_offset[k] = min(base.tiles[0].header.substream_offset[k], 20)
+    _, rc2, st2 = decoder.decode_grids([img2], return_status=True)
+    assert rc2 == K.HEIC_E_BITSTREAM and st2[0].code != 0
+
+
+def test_invalid_descriptors_are_rejected_on_the_host(decoder, heic_file):
+    base = heic_file.primary
+    img, _ = permuted_image(base, list(range(48)))
+    img.n_tiles = 47
+    with pytest.raises(H.HeicError) as e:
+        decoder.decode_grids([img])
+    assert e.value.code == K.HEIC_E_INVALID_ARG
+    img, _ = permuted_image(base, list(range(48)))
+    img.sps.bit_depth_luma_minus8 = 2
+    with pytest.raises(H.HeicError) as e:
+        decoder.decode_grids([img])
+    assert e.value.code == K.HEIC_E_UNSUPPORTED
+
+
+def test_aux_gain_map_monochrome_with_partial_ctbs(decoder, heic_file):
+    """Fixture item 52: a single 2016x1512 hvc1 picture, 4:0:0 — not a multiple of the CTB size, no chroma."""
+    aux = heic_file.aux_images
+    assert len(aux) >= 1
+    img = aux[0]
+    assert img.sps.chroma_format_idc == 0
+    td = img.tiles[0]
+    ref = O.decode_picture(img.sps, img.pps, td.header, (td.rbsp, td.rbsp_len), intermediates=False)
+    (y, _, _), = decoder.decode_grids_yuv([img])
+    w, h = img.output_width, img.output_height
+    assert y.shape == (h, w)
+    assert np.array_equal(y, ref["plane"][0][:h, :w])
+    rgb = decoder.decode_grids([img])[0]
+    assert np.array_equal(rgb[..., 0], rgb[..., 1])  # grey
+
+
+def test_colour_stitch_config2_synthetic_planes(decoder):
+    """BASELINE.json configs[1]: synthetic 8-bit 4:2:0 512x512 grid tiles -> RGB + stitch, bit-exact vs the colour definition."""
+    import torch
+
+    rng = np.random.default_rng(0)
+    n_tiles, tw, th = 48, 512, 512
+    planes = rng.integers(0, 256, n_tiles * tw * th * 3 // 2, dtype=np.uint8)
+    # corner cases in the first tile: all 27 combinations of 0/128/255
+    combos = [(a, b, c) for a in (0, 128, 255) for b in (0, 128, 255) for c in (0, 128, 255)]
+    for i, (yv, cbv, crv) in enumerate(combos):
+        planes[(2 * (i // 16)) * tw + 2 * (i % 16)] = yv
+        planes[tw * th + (i // 16) * (tw // 2) + (i % 16)] = cbv
+        planes[tw * th + (tw // 2) * (th // 2) + (i // 16) * (tw // 2) + (i % 16)] = crv
+    for full_range, mc in [(1, 6), (1, 1), (0, 6), (0, 1)]:
+        ref = O.color_stitch(planes, 6, 8, tw, th, 4032, 3024, full_range, mc)
+        d_planes = torch.from_numpy(planes).cuda()
+        d_rgb = torch.zeros((3024, 4032, 3), dtype=torch.uint8, device="cuda")
+        decoder.color_stitch(d_planes.data_ptr(), 1, 6, 8, tw, th, 4032, 3024, d_rgb.data_ptr(), 4032 * 3, 4032 * 3024 * 3, full_range, mc)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_rgb.cpu().numpy(), ref), (full_range, mc)
+    # ragged canvas: odd crop inside the mosaic
+    ref = O.color_stitch(planes, 6, 8, tw, th, 1001, 777, 1, 6)
+    d_rgb = torch.zeros((777, 1001, 3), dtype=torch.uint8, device="cuda")
+    decoder.color_stitch(d_planes.data_ptr(), 1, 6, 8, tw, th, 1001, 777, d_rgb.data_ptr(), 1001 * 3, 1001 * 777 * 3, 1, 6)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_rgb.cpu().numpy(), ref)
+
+
+def test_launch_accounting(decoder, heic_file):
+    n0 = decoder.launch_count()
+    decoder.decode_grids([heic_file.primary])
+    assert decoder.launch_count() - n0 >= 12  # cabac + 7 transform + intra + deblock + sao + colour
