@@ -108,6 +108,7 @@ struct Engine {
     pos += 4;
   }
   HEIC_HD bool offset_is_illegal() const { return (val >> 22) >= 510u; }
+  HEIC_HD void expect_terminate(int) {}  // hook for the test-only encoder engine (tests/synth); nothing to do when decoding
   HEIC_HD void refill() {
     if (nbits < 7) {
       val |= look0 << (6 - nbits);
@@ -195,9 +196,9 @@ HEIC_HD uint8_t context_init_state(int init_value, int slice_qp) {
 // (1 when a warp serves one substream, 32 when the lanes of a warp serve 32 substreams and their
 // tables are interleaved so that equal context indices fall into one 32-byte row).
 // ------------------------------------------------------------------------------------------------
-template <int STRIDE>
+template <int STRIDE, class Eng = Engine>
 struct Parser {
-  Engine e;
+  Eng e;
   const CabacTabs* T;
   uint8_t* ctx;
   const PicParams* pp;
@@ -755,8 +756,8 @@ HEIC_NO_UNROLL
 //   void abort(int code)                record the failure; every later wait() on this tile returns false
 // Returns the number of CTUs decoded by this thread.
 // ------------------------------------------------------------------------------------------------
-template <int STRIDE, class Sync>
-HEIC_HD uint32_t parse_rows(Parser<STRIDE>& P, const uint32_t* substreams, int slot, int n_slots, Sync& sync) {
+template <int STRIDE, class Eng, class Sync>
+HEIC_HD uint32_t parse_rows(Parser<STRIDE, Eng>& P, const uint32_t* substreams, int slot, int n_slots, Sync& sync) {
   const PicParams* pp = P.pp;
   const TileParams* tp = P.tp;
   const int wpp = pp->wpp, wctb = pp->wctb, hctb = pp->hctb;
@@ -800,9 +801,14 @@ HEIC_HD uint32_t parse_rows(Parser<STRIDE>& P, const uint32_t* substreams, int s
             for (int i = 0; i < NUM_CTX; i++) dst[i * STRIDE] = P.ctx[i * STRIDE];
           }
           const int addr = ry * wctb + rx;
+          P.e.expect_terminate(addr == n_ctb - 1);
           const int end_of_slice = P.e.terminate();  // end_of_slice_segment_flag (slice.rs:214)
-          if (end_of_slice != (addr == n_ctb - 1)) P.fail(-3);
-          else if (wpp && rx == wctb - 1 && !end_of_slice && !P.e.terminate()) P.fail(-3);  // end_of_subset_one_bit (slice.rs:222-227)
+          if (end_of_slice != (addr == n_ctb - 1)) {
+            P.fail(-3);
+          } else if (wpp && rx == wctb - 1 && !end_of_slice) {
+            P.e.expect_terminate(1);
+            if (!P.e.terminate()) P.fail(-3);  // end_of_subset_one_bit (slice.rs:222-227)
+          }
         }
         if (P.err) sync.abort(P.err);
       }
