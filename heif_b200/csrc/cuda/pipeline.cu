@@ -344,6 +344,7 @@ void heic_b200_batch::run(uint32_t mask) {
     CU(cudaMemsetAsync(d_tu.p, 0, tu_words * 4, st));
     CU(cudaMemsetAsync(d_coeff.p, 0, coeff_elems * 2, st));
     CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
+    CU(cudaMemsetAsync(d_sao.p, 0, sao_words * 4, st));  // slices without SAO parse no parameters
     for (const CabacClass& c : classes) {
       CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)d_order.p + c.order_off, c.n_groups, ctx->cabac_tiles_per_cta,
                       c.n_slots, st));
