@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "296")), help="images per GPU per step")
-    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "64")))
+    ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "256")), help="images per reference-facing call")
     ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU arm")
     ap.add_argument("--cpu-images", type=int, default=4, help="images in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
@@ -273,7 +273,7 @@ def main():
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
     eb = min(args.e2e_batch, args.batch)
-    out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8).pin_memory()
+    out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
     d2h = eb * OUT_H * OUT_W * 3

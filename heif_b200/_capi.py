@@ -130,7 +130,7 @@ class TileDump(C.Structure):
 
 
 LIB_NAME = "libheic_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+LIB_PATH = os.environ.get("HEIC_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)  # env: A/B builds
 
 # Every symbol include/heic_b200.h declares: (name, restype, argtypes).
 _vp, _sz = C.c_void_p, C.c_size_t

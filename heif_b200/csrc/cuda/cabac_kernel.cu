@@ -11,7 +11,8 @@
 //
 // R row slots per CTA share the rows of a tile round-robin; with the 2-CTU WPP lag a 16-CTB-wide tile has
 // at most 8 rows in flight, so R = 8 keeps every slot busy.  Rows synchronise through progress counters
-// in shared memory (all rows of a tile live in one CTA, hence on one SM).
+// in shared memory (all rows of a tile live in one CTA, hence on one SM); the per-row context snapshots go
+// through HBM/L2 so that shared memory only holds the live context tables.
 #include <cuda_runtime.h>
 
 #include "cabac_parse.cuh"
@@ -23,6 +24,9 @@ namespace dev {
 namespace {
 
 constexpr int kMaxRows = 512;
+#ifndef HEIC_CABAC_MIN_CTAS
+#define HEIC_CABAC_MIN_CTAS 3  // register budget 80 per thread; 4 (64 regs, more spills) measured equal at batch 592, slower at 296
+#endif
 
 struct CtaShared {
   CabacTabs tabs;
@@ -35,9 +39,10 @@ struct SmemSync {
   volatile int* progress;
   volatile int* aborted;  // this thread's tile
   int* status_code;       // global
-  uint8_t* save_base;     // + (row % R) * NUM_CTX_PAD * TILES
-  uint8_t* ctx_base;      // slot tables, used as save areas when every slot owns exactly one row
-  int n_slots, lane, direct;
+  static constexpr int kSaveStride = 1;
+  uint8_t* save_base;     // this tile's WPP context snapshots in HBM, NUM_CTX_PAD bytes per CTB row (written once and
+                          // read once per row, so they need not occupy shared memory: that is what bounds occupancy)
+  int lane;
 
   __device__ __forceinline__ bool wait(int row, int n) {
     unsigned ns = 32;
@@ -67,12 +72,7 @@ struct SmemSync {
       if (lane == 0) progress[row] = n;
     }
   }
-  __device__ __forceinline__ uint8_t* save_area(int row) {
-    // the snapshot of `row` is consumed by row + 1; with one row per slot it can be written straight into
-    // that row's (still idle) context table
-    if (direct) return ctx_base + (size_t)((row + 1) % n_slots) * NUM_CTX_PAD * TILES;
-    return save_base + (size_t)(row % n_slots) * NUM_CTX_PAD * TILES;
-  }
+  __device__ __forceinline__ uint8_t* save_area(int row) { return save_base + (size_t)row * NUM_CTX_PAD; }
   __device__ __forceinline__ void abort(int code) {
     if (code != -100) atomicCAS(status_code, 0, code);
     *aborted = 1;
@@ -83,12 +83,11 @@ struct SmemSync {
 }  // namespace
 
 template <int TILES>
-__global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? 3 : 1) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
+__global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CABAC_MIN_CTAS : 1) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
                                                     const uint32_t* __restrict__ order, int n_slots) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
   uint8_t* ctx_all = smem_raw + ((sizeof(CtaShared) + 15) & ~(size_t)15);
-  uint8_t* save_all = ctx_all + (size_t)n_slots * NUM_CTX_PAD * TILES;
 
   {  // tables -> shared memory
     const uint32_t* src = reinterpret_cast<const uint32_t*>(gtabs);
@@ -115,9 +114,9 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? 3 : 1) 
   P.pp = pp;
   P.tp = tp;
   P.tu_map = A.tu_map + tp->tu_off;
-  P.coeff[0] = A.coeff + tp->coeff_off[0];
-  P.coeff[1] = A.coeff + tp->coeff_off[1];
-  P.coeff[2] = A.coeff + tp->coeff_off[2];
+  P.coeff0 = A.coeff + tp->coeff_off[0];
+  P.coeff1 = A.coeff + tp->coeff_off[1];
+  P.coeff2 = A.coeff + tp->coeff_off[2];
   P.ipm = A.ipm + tp->map4_off;
   P.ct_depth = A.ct_depth + tp->map8_off;
   P.qp_map = A.qp_map + tp->map8_off;
@@ -129,11 +128,8 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? 3 : 1) 
   sync.progress = sh->progress;
   sync.aborted = &sh->aborted[TILES == 1 ? 0 : lane];
   sync.status_code = &A.status[tile].code;
-  sync.n_slots = n_slots;
   sync.lane = lane;
-  sync.direct = pp->hctb <= n_slots;
-  sync.ctx_base = ctx_all + (TILES == 1 ? 0 : lane);
-  sync.save_base = save_all + (TILES == 1 ? 0 : lane);
+  sync.save_base = A.wpp_save + tp->wpp_off;
   if (!active) *sync.aborted = 1;
 
   const uint32_t ctus = parse_rows<TILES>(P, A.substreams + tp->sub_first, slot, n_slots, sync);
@@ -144,7 +140,7 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? 3 : 1) 
 }
 
 size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
-  return ((sizeof(CtaShared) + 15) & ~(size_t)15) + (size_t)2 * n_slots * NUM_CTX_PAD * tiles_per_cta;
+  return ((sizeof(CtaShared) + 15) & ~(size_t)15) + (size_t)n_slots * NUM_CTX_PAD * tiles_per_cta;
 }
 
 cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,

@@ -36,7 +36,7 @@ struct CabacTabs {
   uint8_t init_value[NUM_CTX_PAD];
 };
 
-#if defined(__CUDACC__)
+#if defined(__CUDA_ARCH__)
 #define HEIC_NO_UNROLL _Pragma("unroll 1")
 #else
 #define HEIC_NO_UNROLL
@@ -204,14 +204,15 @@ struct Parser {
   const PicParams* pp;
   const TileParams* tp;
   uint32_t* tu_map;
-  int16_t* coeff[3];
+  int16_t *coeff0, *coeff1, *coeff2;
   uint8_t *ipm, *ct_depth, *qp_map;
   uint32_t* sao;
   // QP state (8.6.1)
   int is_cu_qp_delta_coded, cu_qp_delta_val, qp_y, last_qp_y, qp_y_pred, first_qg_in_row, qg_x, qg_y;
   // current CU
   int part_nxn, chroma_mode, cu_x, cu_y, cu_log2;
-  int pu_mode[4];
+  uint32_t pu_modes;  // IntraPredModeY of the (up to) four prediction blocks, 8 bits each (no indexed arrays: they
+                      // would live in local memory)
   int err;
 
 #if defined(__CUDA_ARCH__)
@@ -270,7 +271,7 @@ struct Parser {
       p[3] = 0;
       return;
     }
-    uint32_t w[3] = {0, 0, 0};
+    uint32_t w0 = 0, w1 = 0, w2 = 0;
     int type_c = 0, class_c = 0;
     int n_comp = pp->chroma ? 3 : 1;
     for (int c = 0; c < n_comp; c++) {
@@ -284,13 +285,14 @@ struct Parser {
         if (c == 1) type_c = type;
       }
       if (!type) continue;
-      int abs_v[4];
-      for (int i = 0; i < 4; i++) abs_v[i] = (int)e.tr_bypass(7);
+      uint32_t abs4 = 0;  // four sao_offset_abs, 4 bits each
+      for (int i = 0; i < 4; i++) abs4 |= e.tr_bypass(7) << (4 * i);
       uint32_t v = (uint32_t)type;
       if (type == 1) {
         for (int i = 0; i < 4; i++) {
-          int neg = abs_v[i] ? e.bypass() : 0;
-          int o = neg ? -abs_v[i] : abs_v[i];
+          const int a = (int)((abs4 >> (4 * i)) & 15u);
+          const int neg = a ? e.bypass() : 0;
+          const int o = neg ? -a : a;
           v |= ((uint32_t)o & 15u) << (8 + 4 * i);
         }
         v |= e.fl_bypass(5) << 2;  // sao_band_position
@@ -300,16 +302,18 @@ struct Parser {
         else if (c == 1) cl = class_c = (int)e.fl_bypass(2);
         else cl = class_c;
         v |= (uint32_t)cl << 2;
-        v |= ((uint32_t)abs_v[0] & 15u) << 8;
-        v |= ((uint32_t)abs_v[1] & 15u) << 12;
-        v |= ((uint32_t)(-abs_v[2]) & 15u) << 16;
-        v |= ((uint32_t)(-abs_v[3]) & 15u) << 20;
+        v |= (abs4 & 15u) << 8;
+        v |= ((abs4 >> 4) & 15u) << 12;
+        v |= ((uint32_t)(-(int)((abs4 >> 8) & 15u)) & 15u) << 16;
+        v |= ((uint32_t)(-(int)((abs4 >> 12) & 15u)) & 15u) << 20;
       }
-      w[c] = v;
+      if (c == 0) w0 = v;
+      else if (c == 1) w1 = v;
+      else w2 = v;
     }
-    p[0] = w[0];
-    p[1] = w[1];
-    p[2] = w[2];
+    p[0] = w0;
+    p[1] = w1;
+    p[2] = w2;
     p[3] = 0;
   }
 
@@ -364,17 +368,20 @@ struct Parser {
     if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
     int last_x, last_y;
     {
-      int pre[2];
+      uint32_t pre = 0;  // both prefixes, 8 bits each, through one call site
 HEIC_NO_UNROLL
-      for (int d = 0; d < 2; d++) pre[d] = last_sig_coeff_prefix(d ? CTX_LAST_Y : CTX_LAST_X, c_idx, log2);
+      for (int d = 0; d < 2; d++) pre |= (uint32_t)last_sig_coeff_prefix(d ? CTX_LAST_Y : CTX_LAST_X, c_idx, log2) << (8 * d);
 HEIC_NO_UNROLL
-      for (int d = 0; d < 2; d++)  // suffixes follow both prefixes (7.3.8.11)
-        if (pre[d] > 3) {
-          const int nb = (pre[d] >> 1) - 1;
-          pre[d] = (1 << nb) * (2 + (pre[d] & 1)) + (int)e.fl_bypass(nb);
+      for (int d = 0; d < 2; d++) {  // suffixes follow both prefixes (7.3.8.11)
+        const int pv = (int)((pre >> (8 * d)) & 0xffu);
+        if (pv > 3) {
+          const int nb = (pv >> 1) - 1;
+          const int full = (1 << nb) * (2 + (pv & 1)) + (int)e.fl_bypass(nb);
+          pre = (pre & ~(0xffu << (8 * d))) | ((uint32_t)full << (8 * d));
         }
-      last_x = pre[0];
-      last_y = pre[1];
+      }
+      last_x = (int)(pre & 0xffu);
+      last_y = (int)((pre >> 8) & 0xffu);
     }
     int scan_idx = 0;
     if (log2 == 2 || (log2 == 3 && c_idx == 0)) {
@@ -518,7 +525,8 @@ HEIC_NO_UNROLL
   HEIC_HD void transform_unit(int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr,
                               uint32_t ctb_addr, uint32_t z4) {
     const int pb_shift = part_nxn ? cu_log2 - 1 : cu_log2;
-    const int luma_mode = pu_mode[(((x0 - cu_x) >> pb_shift) & 1) | ((((y0 - cu_y) >> pb_shift) & 1) << 1)];
+    const int pu_idx = (((x0 - cu_x) >> pb_shift) & 1) | ((((y0 - cu_y) >> pb_shift) & 1) << 1);
+    const int luma_mode = (int)((pu_modes >> (8 * pu_idx)) & 0xffu);
     const int has_chroma = pp->chroma && (log2 > 2 || blk_idx == 3);
     const int log2c = log2 > 2 ? log2 - 1 : 2;
     const int any_cbf = cbf_luma | cbf_cb | cbf_cr;  // 7.3.8.10: parent-inherited chroma cbfs count for blkIdx 0..2 too
@@ -544,7 +552,7 @@ HEIC_NO_UNROLL
     for (int c = 0; c < 3; c++) {
       const int cbf = c == 0 ? cbf_luma : (c == 1 ? cbf_cb : cbf_cr);
       if (!cbf) continue;
-      int16_t* dst = c == 0 ? coeff[0] + (size_t)ti * 16 : (c == 1 ? coeff[1] : coeff[2]) + off_c;
+      int16_t* dst = c == 0 ? coeff0 + (size_t)ti * 16 : (c == 1 ? coeff1 : coeff2) + off_c;
       ts |= (uint32_t)residual_coding(c ? log2c : log2, c, c ? chroma_mode : luma_mode, dst) << c;
     }
     const int ts0 = (int)(ts & 1u), ts1 = (int)((ts >> 1) & 1u), ts2 = (int)((ts >> 2) & 1u);
@@ -659,26 +667,28 @@ HEIC_NO_UNROLL
       return;
     }
     const int n_pu = part_nxn ? 4 : 1, pb = part_nxn ? n >> 1 : n;
-    int prev[4];
-    for (int k = 0; k < n_pu; k++) prev[k] = dec(CTX_PREV_INTRA);
+    uint32_t prev = 0;  // prev_intra_luma_pred_flag of every prediction block first (7.3.8.5)
+    for (int k = 0; k < n_pu; k++) prev |= (uint32_t)dec(CTX_PREV_INTRA) << k;
+    pu_modes = 0;
     for (int k = 0; k < n_pu; k++) {
       int mpm_idx = 0, rem = 0;
-      if (prev[k]) mpm_idx = (int)e.tr_bypass(2);
+      const int prev_k = (int)((prev >> k) & 1u);
+      if (prev_k) mpm_idx = (int)e.tr_bypass(2);
       else rem = (int)e.fl_bypass(5);
       int px = x0 + (k & 1) * pb, py = y0 + (k >> 1) * pb;
-      int mode = derive_luma_mode(px, py, prev[k], mpm_idx, rem);
-      pu_mode[k] = mode;
+      int mode = derive_luma_mode(px, py, prev_k, mpm_idx, rem);
+      pu_modes |= (uint32_t)mode << (8 * k);
       // neighbours only ever read the right column and the bottom row of a prediction block
       const int b4 = pb >> 2, x4 = px >> 2, y4 = py >> 2;
       for (int j = 0; j < b4; j++) ipm[(y4 + j) * pp->w4 + x4 + b4 - 1] = (uint8_t)mode;
       for (int j = 0; j < b4 - 1; j++) ipm[(y4 + b4 - 1) * pp->w4 + x4 + j] = (uint8_t)mode;
     }
-    if (!part_nxn) pu_mode[1] = pu_mode[2] = pu_mode[3] = pu_mode[0];
+    if (!part_nxn) pu_modes *= 0x01010101u;
     chroma_mode = 0;
     if (pp->chroma) {  // intra_chroma_pred_mode (decoder.rs:23-35,192-204) + 8.4.3
       int idx = 4;
       if (dec(CTX_CHROMA_PRED)) idx = (int)e.fl_bypass(2);
-      const int luma = pu_mode[0];
+      const int luma = (int)(pu_modes & 0xffu);
       if (idx == 4) {
         chroma_mode = luma;
       } else {
@@ -752,7 +762,7 @@ HEIC_NO_UNROLL
 // round-robin; Sync provides the wavefront:
 //   bool wait(int row, int n_ctus)      block until `row` has finished n_ctus CTUs (false: tile aborted)
 //   void publish(int row, int n_ctus)   announce progress of `row`
-//   uint8_t* save_area(int row)         context snapshot of `row` (same STRIDE interleave as ctx)
+//   uint8_t* save_area(int row)         context snapshot of `row`, entries kSaveStride bytes apart
 //   void abort(int code)                record the failure; every later wait() on this tile returns false
 // Returns the number of CTUs decoded by this thread.
 // ------------------------------------------------------------------------------------------------
@@ -788,8 +798,7 @@ HEIC_HD uint32_t parse_rows(Parser<STRIDE, Eng>& P, const uint32_t* substreams, 
             P.init_contexts(tp->slice_qp);
           } else {
             const uint8_t* src = sync.save_area(ry - 1);
-            if (src != P.ctx)
-              for (int i = 0; i < NUM_CTX; i++) P.ctx[i * STRIDE] = src[i * STRIDE];
+            for (int i = 0; i < NUM_CTX; i++) P.st_ctx(i, src[i * Sync::kSaveStride]);
           }
           P.first_qg_in_row = 1;
         }
@@ -798,7 +807,7 @@ HEIC_HD uint32_t parse_rows(Parser<STRIDE, Eng>& P, const uint32_t* substreams, 
           ctus++;
           if (wpp && rx == 1 && ry + 1 < hctb) {
             uint8_t* dst = sync.save_area(ry);
-            for (int i = 0; i < NUM_CTX; i++) dst[i * STRIDE] = P.ctx[i * STRIDE];
+            for (int i = 0; i < NUM_CTX; i++) dst[i * Sync::kSaveStride] = (uint8_t)P.ld_ctx(i);
           }
           const int addr = ry * wctb + rx;
           P.e.expect_terminate(addr == n_ctb - 1);

@@ -102,6 +102,7 @@ struct TileParams {
   uint64_t map4_off;            // bytes: ipm map (w4*h4)
   uint64_t map8_off;            // bytes: ct_depth and qp maps (w8*h8 each)
   uint64_t sao_off;             // uint32 words, 4 per CTB
+  uint64_t wpp_off;             // bytes: WPP context snapshots, NUM_CTX_PAD per CTB row
 };
 
 struct TileStatusDev {
@@ -124,6 +125,7 @@ struct Arenas {
   uint8_t* ct_depth;
   uint8_t* qp_map;
   uint32_t* sao;
+  uint8_t* wpp_save;
   TileStatusDev* status;
   uint32_t n_tiles;
 };

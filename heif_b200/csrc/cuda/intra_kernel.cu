@@ -52,15 +52,8 @@ struct Ctu {
   int strong_flag;
 };
 
-// 6.4.1 z-scan availability restated for a single-slice all-intra picture decoded in CTU raster / wavefront
-// order.  (px, py): sample position in plane coordinates relative to the CTU origin; sub = 1 for 4:2:0 chroma.
-__device__ __forceinline__ bool sample_available(const Ctu& c, int px, int py, int sub) {
-  const int lx = px * (1 << sub), ly = py * (1 << sub);
-  const int X = c.x_ctb + lx, Y = c.y_ctb + ly;
-  if (X < 0 || Y < 0 || X >= c.w || Y >= c.h) return false;
-  if (ly < 0) return true;           // CTB row above (incl. above-right CTU: decode order guarantees it)
-  if (lx < 0) return ly < c.ctb;     // CTU to the left; below this CTB row nothing is decoded yet
-  if (lx >= c.ctb || ly >= c.ctb) return false;
+// Reconstructed-yet test of the 4x4 luma unit containing luma position (lx, ly) of the current CTU.
+__device__ __forceinline__ bool unit_done(const Ctu& c, int lx, int ly) {
   const int bit = (ly >> 2) * c.ctb4 + (lx >> 2);
   return (c.dmask[bit >> 5] >> (bit & 31)) & 1u;
 }
@@ -73,44 +66,32 @@ __device__ __forceinline__ void predict_block(const Ctu& c, int cidx, uint8_t* b
   const int N = 1 << log2, sub = cidx ? 1 : 0, lane = c.lane;
   const int total = 4 * N;  // positions 0 .. 4N: s < 2N left column bottom-up, s = 2N corner, s > 2N top row
   uint8_t* ref = c.ref;
-  // ---- 8.4.4.2.2: availability per 4-sample unit: bits [16 - N/2, 16) left units bottom-up, bit 16 the
-  // corner, bits (16, 16 + N/2] top units left to right ------------------------------------------------
-  uint64_t mask;
+  // ---- 8.4.4.2.2 reference availability (6.4.1) for a single-slice all-intra picture in z-scan order ---------
+  // The left column and the top row exist whenever the block is not on the picture border.  The below-left and
+  // above-right N samples belong to ONE aligned N x N block each, which is either completely reconstructed or not
+  // started (transform units are atomic in z-order), further cut by the picture / CTB-row limits to a prefix.  So the
+  // available samples form one interval [lo, hi] of the scan (bottom-left -> corner -> top-right), and the
+  // substitution process ("nearest available sample before, else first one after") is a clamp of s to that interval.
+  int lo, hi;
   {
-    const int hu = N >> 1;  // units per side
-    bool a = false;
-    if (lane < hu) a = sample_available(c, bx - 1, by + 2 * N - 1 - 4 * lane, sub);
-    else if (lane < N) a = sample_available(c, bx + 4 * (lane - hu), by - 1, sub);
-    const uint32_t bal = __ballot_sync(0xffffffffu, a);
-    const uint64_t left = bal & ((1u << hu) - 1u), top = (bal >> hu) & ((1u << hu) - 1u);
-    const uint64_t corner = sample_available(c, bx - 1, by - 1, sub) ? 1u : 0u;
-    mask = (left << (16 - hu)) | (corner << 16) | (top << 17);
+    const int cs = c.ctb >> sub;
+    const int X0 = (c.x_ctb >> sub) + bx, Y0 = (c.y_ctb >> sub) + by;
+    const bool left_ok = X0 > 0, top_ok = Y0 > 0;
+    int n_bl = 0, n_tr = 0;
+    if (left_ok && by + N < cs && (bx == 0 || unit_done(c, (bx - 1) << sub, (by + N) << sub)))
+      n_bl = min(N, max(0, (c.h >> sub) - (Y0 + N)));
+    if (top_ok && (by == 0 || (bx + N < cs && unit_done(c, (bx + N) << sub, (by - 1) << sub))))
+      n_tr = min(N, max(0, (c.w >> sub) - (X0 + N)));
+    lo = left_ok ? N - n_bl : 2 * N + 1;
+    hi = top_ok ? 3 * N + n_tr : 2 * N - 1;  // lo > hi: nothing available -> 1 << (bitDepth - 1)
   }
-  const int base_bit = 16 - (N >> 1);
 #pragma unroll 1
   for (int s0 = 0; s0 <= total; s0 += 32) {
     const int s = s0 + lane;
     if (s <= total) {
-      // unit of sample s and the sample that stands in for it when the unit is unavailable
-      int bit = s < 2 * N ? base_bit + (s >> 2) : (s == 2 * N ? 16 : 17 + ((s - 2 * N - 1) >> 2));
-      int src = s;
       int v = 128;
-      if (mask) {
-        if (!((mask >> bit) & 1ull)) {
-          const uint64_t lower = mask & ((1ull << bit) - 1ull);
-          int sb;
-          bool last;  // take the last (true) or first (false) sample of unit sb
-          if (lower) {
-            sb = 63 - __clzll(lower);
-            last = true;
-          } else {
-            sb = bit + __ffsll(mask >> (bit + 1));
-            last = false;
-          }
-          if (sb < 16) src = 4 * (sb - base_bit) + (last ? 3 : 0);
-          else if (sb == 16) src = 2 * N;
-          else src = 2 * N + 1 + 4 * (sb - 17) + (last ? 3 : 0);
-        }
+      if (lo <= hi) {
+        const int src = min(max(s, lo), hi);
         const int dx = src <= 2 * N ? -1 : src - 2 * N - 1;
         const int dy = src <= 2 * N ? 2 * N - 1 - src : -1;
         v = buf[(by + dy + 1) * stride + bx + dx + 16];

@@ -92,7 +92,12 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
-  std::unique_ptr<heic_b200_batch> scratch;
+  // decode_grids pipeline: chunks of `pipe_chunk` images rotate over kPipe slots, each with its own stream and
+  // scratch batch, so the H2D copy, the kernels and the D2H copy of different chunks overlap
+  static constexpr int kPipe = 4;
+  int pipe_chunk = 32;
+  cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  std::unique_ptr<heic_b200_batch> pipe_batch[kPipe];
   ~heic_b200_ctx();
 };
 
@@ -109,6 +114,7 @@ struct CabacClass {  // tiles launched together: same wavefront shape
 
 struct heic_b200_batch {
   heic_b200_ctx* ctx = nullptr;
+  cudaStream_t stream = nullptr;  // ctx->stream for explicit batches, a pipeline stream for decode_grids chunks
   bool apply_transforms = false;
   std::vector<PicParams> pics;
   std::vector<ScalingSet> scaling;
@@ -116,21 +122,23 @@ struct heic_b200_batch {
   std::vector<ImageInfo> images;
   std::vector<uint32_t> substreams, order;
   std::vector<CabacClass> classes;
-  size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0;
+  size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0, wpp_bytes = 0;
   size_t rgb_pitch = 0, rgb_image_stride = 0;
   uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
   int max_log2_ctb = 4, max_log2_tb = 2, intra_slots = 1, max_hctb = 1;
   uint32_t stages_run = 0;
-  PinnedBuf h_bitstream, h_status;
-  DevBuf d_bitstream, d_substreams, d_order, d_pics, d_tiles, d_scaling, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
-      d_qp, d_sao, d_status, d_rgb;
+  PinnedBuf h_bitstream, h_status, h_params;
+  size_t off_sub = 0, off_order = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
+  DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
+      d_qp, d_sao, d_wpp, d_status, d_rgb;
   Arenas arenas() const {
     Arenas a;
     a.bitstream = (const uint8_t*)d_bitstream.p;
-    a.substreams = (const uint32_t*)d_substreams.p;
-    a.pics = (const PicParams*)d_pics.p;
-    a.tiles = (const TileParams*)d_tiles.p;
-    a.scaling = (const ScalingSet*)d_scaling.p;
+    const uint8_t* pb = (const uint8_t*)d_params.p;
+    a.substreams = (const uint32_t*)(pb + off_sub);
+    a.pics = (const PicParams*)(pb + off_pics);
+    a.tiles = (const TileParams*)(pb + off_tiles);
+    a.scaling = (const ScalingSet*)(pb + off_scaling);
     a.tu_map = (uint32_t*)d_tu.p;
     a.coeff = (int16_t*)d_coeff.p;
     a.recon = (uint8_t*)d_recon.p;
@@ -139,6 +147,7 @@ struct heic_b200_batch {
     a.ct_depth = (uint8_t*)d_ctd.p;
     a.qp_map = (uint8_t*)d_qp.p;
     a.sao = (uint32_t*)d_sao.p;
+    a.wpp_save = (uint8_t*)d_wpp.p;
     a.status = (TileStatusDev*)d_status.p;
     a.n_tiles = (uint32_t)tiles.size();
     return a;
@@ -148,7 +157,10 @@ struct heic_b200_batch {
 };
 
 heic_b200_ctx::~heic_b200_ctx() {
-  scratch.reset();
+  for (int i = 0; i < kPipe; i++) {
+    pipe_batch[i].reset();
+    if (pipe_stream[i]) cudaStreamDestroy(pipe_stream[i]);
+  }
   if (d_tabs) cudaFree(d_tabs);
   if (stream) cudaStreamDestroy(stream);
 }
@@ -162,7 +174,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   substreams.clear();
   order.clear();
   classes.clear();
-  bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = 0;
+  bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = wpp_bytes = 0;
   max_tu = max_w = max_h = max_pitch = 0;
   max_log2_ctb = 4;
   max_log2_tb = 2;
@@ -236,6 +248,8 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       map8_bytes = up(map8_bytes + (size_t)pp.w8 * pp.h8, 64);
       tp.sao_off = sao_words;
       sao_words += (size_t)pp.wctb * pp.hctb * 4;
+      tp.wpp_off = wpp_bytes;
+      wpp_bytes += (size_t)pp.hctb * NUM_CTX_PAD;
       tiles.push_back(tp);
       (void)ctb4;
     }
@@ -298,22 +312,37 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     classes.push_back(c);
   }
 
-  // ---- device memory + uploads -----------------------------------------------------------------------
-  cudaStream_t st = ctx->stream;
+  // ---- device memory + uploads: one pinned blob for all parameter tables, one for the slice data ------------------
+  cudaStream_t st = stream;
   h_bitstream.ensure(bs_bytes + 16);
-  std::memset(h_bitstream.p, 0, bs_bytes + 16);
   {
     size_t t = 0;
+    uint8_t* hb = (uint8_t*)h_bitstream.p;
     for (uint32_t i = 0; i < n_imgs; i++)
-      for (uint32_t k = 0; k < imgs[i].n_tiles; k++, t++)
-        std::memcpy((uint8_t*)h_bitstream.p + tiles[t].bs_off, imgs[i].tiles[k].rbsp, imgs[i].tiles[k].rbsp_len);
+      for (uint32_t k = 0; k < imgs[i].n_tiles; k++, t++) {
+        std::memcpy(hb + tiles[t].bs_off, imgs[i].tiles[k].rbsp, imgs[i].tiles[k].rbsp_len);
+        const size_t end = tiles[t].bs_off + imgs[i].tiles[k].rbsp_len;
+        const size_t next = t + 1 < tiles.size() ? tiles[t + 1].bs_off : bs_bytes + 16;
+        std::memset(hb + end, 0, next - end);
+      }
+  }
+  off_sub = 0;
+  off_order = up(off_sub + substreams.size() * 4, 256);
+  off_pics = up(off_order + order.size() * 4, 256);
+  off_tiles = up(off_pics + pics.size() * sizeof(PicParams), 256);
+  off_scaling = up(off_tiles + tiles.size() * sizeof(TileParams), 256);
+  const size_t params_bytes = up(off_scaling + scaling.size() * sizeof(ScalingSet), 256);
+  h_params.ensure(params_bytes);
+  {
+    uint8_t* hp = (uint8_t*)h_params.p;
+    std::memcpy(hp + off_sub, substreams.data(), substreams.size() * 4);
+    std::memcpy(hp + off_order, order.data(), order.size() * 4);
+    std::memcpy(hp + off_pics, pics.data(), pics.size() * sizeof(PicParams));
+    std::memcpy(hp + off_tiles, tiles.data(), tiles.size() * sizeof(TileParams));
+    std::memcpy(hp + off_scaling, scaling.data(), scaling.size() * sizeof(ScalingSet));
   }
   d_bitstream.ensure(bs_bytes + 16);
-  d_substreams.ensure(substreams.size() * 4);
-  d_order.ensure(order.size() * 4);
-  d_pics.ensure(pics.size() * sizeof(PicParams));
-  d_tiles.ensure(tiles.size() * sizeof(TileParams));
-  d_scaling.ensure(scaling.size() * sizeof(ScalingSet));
+  d_params.ensure(params_bytes);
   d_tu.ensure(tu_words * 4);
   d_coeff.ensure(coeff_elems * 2);
   d_recon.ensure(plane_bytes);
@@ -322,21 +351,17 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   d_ctd.ensure(map8_bytes);
   d_qp.ensure(map8_bytes);
   d_sao.ensure(sao_words * 4);
+  d_wpp.ensure(wpp_bytes);
   d_status.ensure(tiles.size() * sizeof(TileStatusDev));
   h_status.ensure(tiles.size() * sizeof(TileStatusDev));
   if (with_rgb) d_rgb.ensure(rgb_image_stride * images.size());
   CU(cudaMemcpyAsync(d_bitstream.p, h_bitstream.p, bs_bytes + 16, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_substreams.p, substreams.data(), substreams.size() * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_pics.p, pics.data(), pics.size() * sizeof(PicParams), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_tiles.p, tiles.data(), tiles.size() * sizeof(TileParams), cudaMemcpyHostToDevice, st));
-  CU(cudaMemcpyAsync(d_scaling.p, scaling.data(), scaling.size() * sizeof(ScalingSet), cudaMemcpyHostToDevice, st));
-  // the host vectors above are pageable: the copies have completed (staged) when cudaMemcpyAsync returns
+  CU(cudaMemcpyAsync(d_params.p, h_params.p, params_bytes, cudaMemcpyHostToDevice, st));
 }
 
 // ---- stage sequencing ----------------------------------------------------------------------------------
 void heic_b200_batch::run(uint32_t mask) {
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = stream;
   const Arenas A = arenas();
   if (!A.n_tiles) return;
   if (mask & HEIC_STAGE_CABAC) {
@@ -346,7 +371,7 @@ void heic_b200_batch::run(uint32_t mask) {
     CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
     CU(cudaMemsetAsync(d_sao.p, 0, sao_words * 4, st));  // slices without SAO parse no parameters
     for (const CabacClass& c : classes) {
-      CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)d_order.p + c.order_off, c.n_groups, ctx->cabac_tiles_per_cta,
+      CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, ctx->cabac_tiles_per_cta,
                       c.n_slots, st));
       ctx->launches++;
     }
@@ -419,7 +444,7 @@ void heic_b200_batch::run(uint32_t mask) {
 namespace {
 
 void collect_status(heic_b200_batch* b, heic_tile_status* status) {
-  cudaStream_t st = b->ctx->stream;
+  cudaStream_t st = b->stream;
   const size_t n = b->tiles.size();
   CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, n * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
@@ -461,6 +486,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_slots = env_int("HEIC_B200_CABAC_SLOTS", 0);
     c->intra_slots = std::min(8, env_int("HEIC_B200_INTRA_SLOTS", 0));
     c->cabac_group_factor = std::max(1, env_int("HEIC_B200_CABAC_GROUP_FACTOR", 1));
+    c->pipe_chunk = std::max(1, env_int("HEIC_B200_PIPE_CHUNK", 32));
     *out_ctx = c.release();
     return 0;
   }));
@@ -482,6 +508,7 @@ int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, 
     CU(cudaSetDevice(ctx->device));
     auto b = std::make_unique<heic_b200_batch>();
     b->ctx = ctx;
+    b->stream = ctx->stream;
     b->apply_transforms = false;
     b->load(imgs, n_imgs, true);
     CU(cudaStreamSynchronize(ctx->stream));
@@ -493,7 +520,7 @@ int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, 
 void heic_b200_batch_destroy(heic_b200_batch* b) {
   if (!b) return;
   cudaSetDevice(b->ctx->device);
-  cudaStreamSynchronize(b->ctx->stream);
+  cudaStreamSynchronize(b->stream);
   delete b;
 }
 
@@ -511,12 +538,12 @@ int32_t heic_b200_batch_decode(heic_b200_batch* b) { return heic_b200_batch_run_
 int32_t heic_b200_batch_sync(heic_b200_batch* b) {
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!b) bail(HEIC_E_INVALID_ARG, "null batch");
-    CU(cudaStreamSynchronize(b->ctx->stream));
+    CU(cudaStreamSynchronize(b->stream));
     return 0;
   }));
 }
 
-void* heic_b200_batch_stream(heic_b200_batch* b) { return b ? (void*)b->ctx->stream : nullptr; }
+void* heic_b200_batch_stream(heic_b200_batch* b) { return b ? (void*)b->stream : nullptr; }
 
 int32_t heic_b200_batch_rgb(heic_b200_batch* b, void** dev_ptr, size_t* pitch, size_t* image_stride) {
   if (!b) {
@@ -533,7 +560,7 @@ int32_t heic_b200_batch_download_rgb(heic_b200_batch* b, uint8_t* rgb_out, size_
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!b || !rgb_out) bail(HEIC_E_INVALID_ARG, "null argument");
     CU(cudaSetDevice(b->ctx->device));
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = b->stream;
     for (size_t i = 0; i < b->images.size(); i++) {
       const ImageInfo& im = b->images[i];
       if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
@@ -560,7 +587,7 @@ int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!b || !dump || tile_index >= b->tiles.size()) bail(HEIC_E_INVALID_ARG, "invalid argument");
     CU(cudaSetDevice(b->ctx->device));
-    cudaStream_t st = b->ctx->stream;
+    cudaStream_t st = b->stream;
     CU(cudaStreamSynchronize(st));
     const TileParams& tp = b->tiles[tile_index];
     const PicParams& pp = b->pics[tp.pic];
@@ -597,63 +624,118 @@ int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_
 }
 
 // HOST in / HOST out: the reference-facing call (replaces the tile loop of decoder.rs:98-119).
+// The images are processed in chunks that rotate over kPipe (stream, scratch batch) slots: while chunk k's RGB
+// travels to the host, chunk k+1 runs its kernels and chunk k+2's slice data travels to the device.  Output buffers
+// should be pinned host memory; pageable memory works but its copies are staged synchronously.
 static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
                                  size_t pitch, size_t image_stride, int32_t apply_transforms, uint8_t* y_out,
                                  uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
   if (!ctx || !imgs || !n_imgs) bail(HEIC_E_INVALID_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));
-  if (!ctx->scratch) {
-    ctx->scratch = std::make_unique<heic_b200_batch>();
-    ctx->scratch->ctx = ctx;
-  }
-  heic_b200_batch* b = ctx->scratch.get();
-  b->apply_transforms = apply_transforms != 0;
-  b->load(imgs, n_imgs, rgb_out != nullptr);
-  cudaStream_t st = ctx->stream;
-  b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
-  if (rgb_out) {
-    for (size_t i = 0; i < b->images.size(); i++) {
-      const ImageInfo& im = b->images[i];
-      if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
-      CU(cudaMemcpy2DAsync(rgb_out + i * image_stride, pitch, (const uint8_t*)b->d_rgb.p + i * b->rgb_image_stride,
-                           b->rgb_pitch, (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, st));
-    }
-  } else {
-    // planar output: tile mosaic cropped to the canvas, images back to back
-    size_t yo = 0, co = 0;
-    for (size_t i = 0; i < b->images.size(); i++) {
-      const ImageInfo& im = b->images[i];
-      const PicParams& pp = b->pics[im.pic];
-      const size_t cw = (im.out_w + 1) / 2, chh = (im.out_h + 1) / 2;
-      for (uint32_t t = 0; t < im.n_tiles; t++) {
-        const TileParams& tp = b->tiles[im.first_tile + t];
-        const size_t tx = (size_t)(t % im.grid_cols) * pp.w, ty = (size_t)(t / im.grid_cols) * pp.h;
-        if (tx >= im.out_w || ty >= im.out_h) continue;
-        const size_t w = std::min<size_t>(pp.w, im.out_w - tx), h = std::min<size_t>(pp.h, im.out_h - ty);
-        CU(cudaMemcpy2DAsync(y_out + yo + ty * im.out_w + tx, im.out_w, (const uint8_t*)b->d_final.p + tp.plane_off[0],
-                             pp.pitch_y, w, h, cudaMemcpyDeviceToHost, st));
-        if (pp.chroma && cb_out && cr_out) {
-          const size_t wc = std::min<size_t>(pp.w / 2, cw - tx / 2), hc = std::min<size_t>(pp.h / 2, chh - ty / 2);
-          CU(cudaMemcpy2DAsync(cb_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[1],
-                               pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
-          CU(cudaMemcpy2DAsync(cr_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[2],
-                               pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
-        }
-      }
-      yo += (size_t)im.out_w * im.out_h;
-      co += cw * chh;
-    }
+  // validate every descriptor before any work is queued, so a bad image rejects the call as a whole
+  std::vector<size_t> first_tile(n_imgs + 1, 0), y_off(n_imgs + 1, 0), c_off(n_imgs + 1, 0);
+  for (uint32_t i = 0; i < n_imgs; i++) {
+    const heic_image_desc& im = imgs[i];
+    if (!im.tiles || im.n_tiles == 0 || im.n_tiles != im.grid_rows * im.grid_cols)
+      bail(HEIC_E_INVALID_ARG, "image descriptor: n_tiles must equal grid_rows * grid_cols");
+    PicParams pp;
+    make_pic_params(im.sps, im.pps, pp);
+    TileParams tp;
+    for (uint32_t t = 0; t < im.n_tiles; t++) make_tile_params(pp, im.pps, im.tiles[t], tp);
+    const size_t ow = im.output_width ? im.output_width : (size_t)im.grid_cols * pp.w;
+    const size_t oh = im.output_height ? im.output_height : (size_t)im.grid_rows * pp.h;
+    first_tile[i + 1] = first_tile[i] + im.n_tiles;
+    y_off[i + 1] = y_off[i] + ow * oh;
+    c_off[i + 1] = c_off[i] + ((ow + 1) / 2) * ((oh + 1) / 2);
   }
   std::vector<heic_tile_status> local;
-  heic_tile_status* s = status;
-  if (!s) {
-    local.resize(b->tiles.size());
-    s = local.data();
+  heic_tile_status* s_out = status;
+  if (!s_out) {
+    local.resize(first_tile[n_imgs]);
+    s_out = local.data();
   }
-  collect_status(b, s);  // synchronises the stream
-  int bad = 0;
-  for (size_t i = 0; i < b->tiles.size(); i++)
-    if (s[i].code != 0) bad++;
+  const uint32_t chunk = (uint32_t)std::max(1, ctx->pipe_chunk);
+  const uint32_t n_chunks = (n_imgs + chunk - 1) / chunk;
+  struct Pending {
+    bool busy = false;
+    size_t tile0 = 0, n_tiles = 0;
+  } pending[heic_b200_ctx::kPipe];
+  auto harvest = [&](int slot) {
+    Pending& pd = pending[slot];
+    if (!pd.busy) return;
+    heic_b200_batch* b = ctx->pipe_batch[slot].get();
+    CU(cudaStreamSynchronize(b->stream));
+    const TileStatusDev* s = (const TileStatusDev*)b->h_status.p;
+    for (size_t i = 0; i < pd.n_tiles; i++) {
+      s_out[pd.tile0 + i].code = s[i].code;
+      s_out[pd.tile0 + i].bins_decoded = s[i].bins;
+      s_out[pd.tile0 + i].ctus_decoded = s[i].ctus;
+      s_out[pd.tile0 + i].reserved = 0;
+    }
+    pd.busy = false;
+  };
+  for (uint32_t k = 0; k < n_chunks; k++) {
+    const int slot = (int)(k % heic_b200_ctx::kPipe);
+    const uint32_t i0 = k * chunk, cnt = std::min(chunk, n_imgs - i0);
+    if (!ctx->pipe_stream[slot]) CU(cudaStreamCreateWithFlags(&ctx->pipe_stream[slot], cudaStreamNonBlocking));
+    if (!ctx->pipe_batch[slot]) {
+      ctx->pipe_batch[slot] = std::make_unique<heic_b200_batch>();
+      ctx->pipe_batch[slot]->ctx = ctx;
+      ctx->pipe_batch[slot]->stream = ctx->pipe_stream[slot];
+    }
+    harvest(slot);  // the slot's previous chunk (kernels, copies, status) is complete before its buffers are reused
+    heic_b200_batch* b = ctx->pipe_batch[slot].get();
+    cudaStream_t st = b->stream;
+    b->apply_transforms = apply_transforms != 0;
+    b->load(imgs + i0, cnt, rgb_out != nullptr);
+    b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
+    if (rgb_out) {
+      bool one_copy = image_stride == b->rgb_image_stride && pitch == b->rgb_pitch;
+      for (size_t i = 0; i < b->images.size() && one_copy; i++)
+        one_copy = (size_t)b->images[i].rot_w * 3 == pitch && (size_t)b->images[i].rot_h * pitch == image_stride;
+      if (one_copy) {
+        CU(cudaMemcpyAsync(rgb_out + (size_t)i0 * image_stride, b->d_rgb.p, (size_t)cnt * image_stride, cudaMemcpyDeviceToHost, st));
+      } else {
+        for (size_t i = 0; i < b->images.size(); i++) {
+          const ImageInfo& im = b->images[i];
+          if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+          CU(cudaMemcpy2DAsync(rgb_out + (i0 + i) * image_stride, pitch, (const uint8_t*)b->d_rgb.p + i * b->rgb_image_stride,
+                               b->rgb_pitch, (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, st));
+        }
+      }
+    } else {
+      // planar output: tile mosaic cropped to the canvas, images back to back
+      for (size_t i = 0; i < b->images.size(); i++) {
+        const ImageInfo& im = b->images[i];
+        const PicParams& pp = b->pics[im.pic];
+        const size_t yo = y_off[i0 + i], co = c_off[i0 + i];
+        const size_t cw = (im.out_w + 1) / 2, chh = (im.out_h + 1) / 2;
+        for (uint32_t t = 0; t < im.n_tiles; t++) {
+          const TileParams& tp = b->tiles[im.first_tile + t];
+          const size_t tx = (size_t)(t % im.grid_cols) * pp.w, ty = (size_t)(t / im.grid_cols) * pp.h;
+          if (tx >= im.out_w || ty >= im.out_h) continue;
+          const size_t w = std::min<size_t>(pp.w, im.out_w - tx), h = std::min<size_t>(pp.h, im.out_h - ty);
+          CU(cudaMemcpy2DAsync(y_out + yo + ty * im.out_w + tx, im.out_w, (const uint8_t*)b->d_final.p + tp.plane_off[0],
+                               pp.pitch_y, w, h, cudaMemcpyDeviceToHost, st));
+          if (pp.chroma && cb_out && cr_out) {
+            const size_t wc = std::min<size_t>(pp.w / 2, cw - tx / 2), hc = std::min<size_t>(pp.h / 2, chh - ty / 2);
+            CU(cudaMemcpy2DAsync(cb_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[1],
+                                 pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpy2DAsync(cr_out + co + (ty / 2) * cw + tx / 2, cw, (const uint8_t*)b->d_final.p + tp.plane_off[2],
+                                 pp.pitch_c, wc, hc, cudaMemcpyDeviceToHost, st));
+          }
+        }
+      }
+    }
+    CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, b->tiles.size() * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
+    pending[slot].busy = true;
+    pending[slot].tile0 = first_tile[i0];
+    pending[slot].n_tiles = b->tiles.size();
+  }
+  for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++) harvest(slot);
+  size_t bad = 0;
+  for (size_t i = 0; i < first_tile[n_imgs]; i++)
+    if (s_out[i].code != 0) bad++;
   if (bad) {
     set_last_error(std::to_string(bad) + " tile(s) failed to decode (malformed slice data); see the per-tile status");
     return HEIC_E_BITSTREAM;

@@ -14,6 +14,7 @@ using namespace heic::dev;
 
 namespace {
 struct SeqSync {
+  static constexpr int kSaveStride = 1;
   std::vector<uint8_t> save;
   SeqSync() : save(NUM_CTX_PAD) {}
   bool wait(int, int) { return true; }
@@ -60,9 +61,9 @@ extern "C" int emul_parse_picture(const heic_sps* sps, const heic_pps* pps, cons
       P.pp = &pp;
       P.tp = &tp;
       P.tu_map = tu_map;
-      P.coeff[0] = lvl0;
-      P.coeff[1] = lvl1;
-      P.coeff[2] = lvl2;
+      P.coeff0 = lvl0;
+      P.coeff1 = lvl1;
+      P.coeff2 = lvl2;
       P.ipm = ipm.data();
       P.ct_depth = ctd.data();
       P.qp_map = qp.data();

@@ -189,6 +189,7 @@ struct EncEngine {
 };
 
 struct SeqSync {
+  static constexpr int kSaveStride = 1;
   std::vector<uint8_t> save;
   SeqSync() : save(NUM_CTX_PAD) {}
   bool wait(int, int) { return true; }
@@ -376,9 +377,9 @@ int synth_encode_picture(const synth_config* cfg, uint64_t seed, uint8_t* out_vp
     P.pp = &pp;
     P.tp = &tp;
     P.tu_map = tu.data();
-    P.coeff[0] = l0.data();
-    P.coeff[1] = l1.data();
-    P.coeff[2] = l2.data();
+    P.coeff0 = l0.data();
+    P.coeff1 = l1.data();
+    P.coeff2 = l2.data();
     P.ipm = ipm.data();
     P.ct_depth = ctd.data();
     P.qp_map = qp.data();
