@@ -15,6 +15,8 @@
 // through HBM/L2 so that shared memory only holds the live context tables.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "cabac_parse.cuh"
 #include "kernels.h"
 
@@ -146,7 +148,10 @@ size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
 cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,
                          int tiles_per_cta, int n_slots, cudaStream_t stream) {
   if (!n_groups) return cudaSuccess;
-  const size_t smem = cabac_smem_bytes(tiles_per_cta, n_slots);
+  // Experiment knob: extra (unused) dynamic shared memory per CTA caps the CTAs per SM, leaving registers for
+  // kernels of another stream to co-reside with this latency-bound one.
+  static const size_t pad = []() { const char* e = getenv("HEIC_B200_CABAC_SMEM_PAD"); return e ? (size_t)atol(e) : (size_t)0; }();
+  const size_t smem = cabac_smem_bytes(tiles_per_cta, n_slots) + pad;
   const int threads = 32 * n_slots;
   if (tiles_per_cta == 32) {
     static bool attr_set = false;
