@@ -23,8 +23,10 @@ namespace dev {
 struct CabacTabs {
   // per context state s = pStateIdx<<1|valMps: .x = rangeTabLps[p][0..3] as 4 bytes (Table 9-46),
   // .y = next state after an MPS | next state after an LPS << 8 (Table 9-45, valMps flip folded in)
-  uint32_t st_lps[128];
-  uint32_t st_next[128];
+  struct alignas(8) State {
+    uint32_t lps;   // rangeTabLps[p][0..3], one byte each
+    uint32_t next;  // next state after an MPS | next state after an LPS << 8
+  } st[128];        // one 8-byte entry per state: a single 64-bit shared-memory load per bin
   uint8_t diag4[16];      // 6.5.3 up-right diagonal, 4x4: scan pos -> x | y << 2
   uint8_t diag8[64];      // 8x8: x | y << 3
   uint8_t diag2[4];       // 2x2: x | y << 1
@@ -33,6 +35,9 @@ struct CabacTabs {
   uint8_t inv_diag2[4];
   uint8_t sig_map4[16];   // ctxIdxMap of 9.3.4.2.5 for 4x4 blocks
   uint8_t sig_pat[4][16]; // sigCtx by prevCsbf pattern and yP << 2 | xP (9.3.4.2.5)
+  // sigCtx of the 16 scan positions of a sub-block as nibbles (nibble k = scan position k), before the size / colour
+  // offsets: [scanIdx] for 4x4 blocks (ctxIdxMap), [3 + scanIdx * 4 + prevCsbf] for larger ones
+  uint64_t sig_nib[15];
   uint8_t init_value[NUM_CTX_PAD];
 };
 
@@ -121,8 +126,9 @@ struct Engine {
   // 9.3.4.3.2 (arithmetic.rs:97-135) on a context state s = pStateIdx << 1 | valMps; returns the bin and
   // the updated state through s.
   HEIC_HD int decision(const CabacTabs* T, uint32_t& s) {
-    const uint32_t lps4 = T->st_lps[s];
-    uint32_t nx = T->st_next[s];
+    const CabacTabs::State st = T->st[s];
+    const uint32_t lps4 = st.lps;
+    uint32_t nx = st.next;
     const uint32_t q = (range >> 6) & 3u;
     const uint32_t lps = (lps4 >> (q << 3)) & 0xffu;
     range -= lps;
@@ -421,21 +427,18 @@ HEIC_NO_UNROLL
       }
       if (coded) {
         const int prev_csbf = right | (below << 1);
-        const int sb_off = (c_idx == 0 && (xs | ys)) ? 3 : 0;
-        for (int k = n_start; k >= 0; k--) {
-          if (k > 0 || !infer_sb_dc) {
-            uint32_t pxy = scan_xy(scan_idx, 2, k);
-            int xp = (int)(pxy & 15u), yp = (int)(pxy >> 4);
-            int sig_ctx;
-            if (log2 == 2) sig_ctx = tabs()->sig_map4[(yp << 2) + xp];
-            else if ((xs | ys | xp | yp) == 0) sig_ctx = 0;
-            else sig_ctx = tabs()->sig_pat[prev_csbf][(yp << 2) | xp] + sb_off + sig_off;
-            if (dec(sig_base + sig_ctx)) {
-              sig |= 1u << k;
-              infer_sb_dc = 0;
-            }
+        // sigCtx (9.3.4.2.5) of all 16 scan positions of this sub-block as one word of nibbles + one additive term
+        const uint64_t nib = tabs()->sig_nib[log2 == 2 ? scan_idx : 3 + scan_idx * 4 + prev_csbf];
+        const int add = sig_base + (log2 == 2 ? 0 : ((c_idx == 0 && (xs | ys)) ? 3 : 0) + sig_off);
+        for (int k = n_start; k > 0; k--)
+          if (dec(add + (int)((nib >> (4 * k)) & 15u))) sig |= 1u << k;
+        if (n_start >= 0) {
+          if (infer_sb_dc && sig == 0) {
+            sig = 1u;  // inferred DC of a coded sub-block with no other significant coefficient
           } else {
-            sig |= 1u;  // inferred DC of a coded sub-block with no other significant coefficient
+            // the DC coefficient of the whole block has its own context (sigCtx 0)
+            const int ctx0 = (log2 > 2 && i == 0) ? sig_base : add + (int)(nib & 15u);
+            if (dec(ctx0)) sig |= 1u;
           }
         }
       }

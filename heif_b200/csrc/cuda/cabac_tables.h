@@ -58,11 +58,11 @@ inline void build_cabac_tabs(CabacTabs& t) {
   std::memset(&t, 0, sizeof t);
   for (int s = 0; s < 128; s++) {
     int p = s >> 1, mps = s & 1;
-    t.st_lps[s] = (uint32_t)kRangeTabLps[p][0] | ((uint32_t)kRangeTabLps[p][1] << 8) |
+    t.st[s].lps = (uint32_t)kRangeTabLps[p][0] | ((uint32_t)kRangeTabLps[p][1] << 8) |
                   ((uint32_t)kRangeTabLps[p][2] << 16) | ((uint32_t)kRangeTabLps[p][3] << 24);
     int p_mps = p < 62 ? p + 1 : p;  // transIdxMps
     int mps_after_lps = p == 0 ? 1 - mps : mps;
-    t.st_next[s] = (uint32_t)((p_mps << 1) | mps) | ((uint32_t)((kTransIdxLps[p] << 1) | mps_after_lps) << 8);
+    t.st[s].next = (uint32_t)((p_mps << 1) | mps) | ((uint32_t)((kTransIdxLps[p] << 1) | mps_after_lps) << 8);
   }
   // 6.5.3 up-right diagonal scans
   auto diag = [](int lg, uint8_t* fwd, uint8_t* inv) {
@@ -97,6 +97,23 @@ inline void build_cabac_tabs(CabacTabs& t) {
         else c = 2;
         t.sig_pat[pat][(yp << 2) | xp] = (uint8_t)c;
       }
+  for (int scan = 0; scan < 3; scan++) {
+    auto pos = [&](int k) {  // scan position k -> (xP, yP) of a 4x4 scan (6.5.3-6.5.5)
+      int x, y;
+      if (scan == 0) x = t.diag4[k] & 3, y = t.diag4[k] >> 2;
+      else if (scan == 1) x = k & 3, y = k >> 2;
+      else x = k >> 2, y = k & 3;
+      return (y << 2) | x;
+    };
+    uint64_t w = 0;
+    for (int k = 0; k < 16; k++) w |= (uint64_t)kSigMap4[pos(k)] << (4 * k);
+    t.sig_nib[scan] = w;
+    for (int pat = 0; pat < 4; pat++) {
+      w = 0;
+      for (int k = 0; k < 16; k++) w |= (uint64_t)t.sig_pat[pat][pos(k)] << (4 * k);
+      t.sig_nib[3 + scan * 4 + pat] = w;
+    }
+  }
   std::memcpy(t.init_value, kInitValues, NUM_CTX);
 }
 

@@ -21,38 +21,56 @@ struct Coeffs {
 
 __device__ __forceinline__ uint32_t clip8(int v) { return (uint32_t)min(255, max(0, v)); }
 
-// A thread converts a 4 x 2 block of the canvas (two rows share one row of chroma).
-// grid: flat over (image, pair of canvas rows, block of 4-pixel groups).
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// A thread converts an 8 x 2 block of the canvas (two rows share one row of chroma): 16 + 8 bytes in, 48 bytes out.
+// FULL: full-range input, where (256 Y + t) >> 8 == Y + (t >> 8), so the chroma terms are computed once per 2x2 quad
+// and a pixel costs an add and a clamp per channel.
+// grid: flat over (image, pair of canvas rows, block of 8-pixel groups).
+template <bool FULL>
 __global__ void __launch_bounds__(256) color_stitch_kernel(ColorJob J, Coeffs K, uint32_t row_pairs, uint32_t xblocks) {
   const uint32_t per_image = row_pairs * xblocks;
   const uint32_t image = blockIdx.x / per_image, rem = blockIdx.x % per_image;
   const uint32_t y = (rem / xblocks) * 2;
-  const uint32_t x = ((rem % xblocks) * blockDim.x + threadIdx.x) * 4;
+  const uint32_t x = ((rem % xblocks) * blockDim.x + threadIdx.x) * 8;
   if (x >= J.out_w || y >= J.out_h) return;
-  // all four pixels lie in one tile: tile widths are multiples of 8
+  // all eight pixels lie in one tile: tile widths are multiples of 8
   const uint32_t tc = x / J.tile_w, tr = y / J.tile_h, lx = x - tc * J.tile_w, ly = y - tr * J.tile_h;
   const uint8_t* t = J.planes + (size_t)(image * J.grid_cols * J.grid_rows + tr * J.grid_cols + tc) * J.tile_stride;
-  const uint32_t y0 = *reinterpret_cast<const uint32_t*>(t + (size_t)ly * J.pitch_y + lx);
   const bool two_rows = y + 1 < J.out_h;  // tile heights are even, so row y + 1 is in the same tile
-  const uint32_t y1 = two_rows ? *reinterpret_cast<const uint32_t*>(t + (size_t)(ly + 1) * J.pitch_y + lx) : 0u;
-  uint32_t cb = 0x8080u, cr = 0x8080u;
+  uint2 yr[2];
+  yr[0] = *reinterpret_cast<const uint2*>(t + (size_t)ly * J.pitch_y + lx);
+  yr[1] = two_rows ? *reinterpret_cast<const uint2*>(t + (size_t)(ly + 1) * J.pitch_y + lx) : make_uint2(0u, 0u);
+  uint32_t cb = 0x80808080u, cr = 0x80808080u;
   if (J.chroma) {
     const size_t co = (size_t)(ly >> 1) * J.pitch_c + (lx >> 1);
-    cb = *reinterpret_cast<const uint16_t*>(t + J.cb_off + co);
-    cr = *reinterpret_cast<const uint16_t*>(t + J.cr_off + co);
+    cb = *reinterpret_cast<const uint32_t*>(t + J.cb_off + co);
+    cr = *reinterpret_cast<const uint32_t*>(t + J.cr_off + co);
   }
-  uint32_t px[2][4][3];
+  uint32_t px[2][8][3];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int c = (int)((cb >> (8 * (i >> 1))) & 0xffu) - 128, d = (int)((cr >> (8 * (i >> 1))) & 0xffu) - 128;
+  for (int j = 0; j < 4; j++) {
+    const int c = (int)((cb >> (8 * j)) & 0xffu) - 128, d = (int)((cr >> (8 * j)) & 0xffu) - 128;
     const int r_add = K.rv * d + 128, g_add = K.gu * c + K.gv * d + 128, b_add = K.bu * c + 128;
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const int yy = K.y_mul * ((int)(((r ? y1 : y0) >> (8 * i)) & 0xffu) - K.y_sub);
-      px[r][i][0] = clip8((yy + r_add) >> 8);
-      px[r][i][1] = clip8((yy + g_add) >> 8);
-      px[r][i][2] = clip8((yy + b_add) >> 8);
-    }
+    for (int r = 0; r < 2; r++)
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        const int p = 2 * j + i;
+        const int Y = (int)(((p < 4 ? yr[r].x : yr[r].y) >> (8 * (p & 3))) & 0xffu);
+        if (FULL) {
+          px[r][p][0] = clip8(Y + (r_add >> 8));
+          px[r][p][1] = clip8(Y + (g_add >> 8));
+          px[r][p][2] = clip8(Y + (b_add >> 8));
+        } else {
+          const int yy = K.y_mul * (Y - K.y_sub);
+          px[r][p][0] = clip8((yy + r_add) >> 8);
+          px[r][p][1] = clip8((yy + g_add) >> 8);
+          px[r][p][2] = clip8((yy + b_add) >> 8);
+        }
+      }
   }
   uint8_t* img = J.rgb + (size_t)image * J.image_stride;
   if (J.rotation == 0) {
@@ -60,15 +78,18 @@ __global__ void __launch_bounds__(256) color_stitch_kernel(ColorJob J, Coeffs K,
     for (int r = 0; r < 2; r++) {
       if (r == 1 && !two_rows) break;
       uint8_t* o = img + (size_t)(y + r) * J.pitch + (size_t)x * 3;
-      if (x + 4 <= J.out_w && (((uintptr_t)o) & 3u) == 0) {
-        uint32_t w0 = px[r][0][0] | (px[r][0][1] << 8) | (px[r][0][2] << 16) | (px[r][1][0] << 24);
-        uint32_t w1 = px[r][1][1] | (px[r][1][2] << 8) | (px[r][2][0] << 16) | (px[r][2][1] << 24);
-        uint32_t w2 = px[r][2][2] | (px[r][3][0] << 8) | (px[r][3][1] << 16) | (px[r][3][2] << 24);
-        reinterpret_cast<uint32_t*>(o)[0] = w0;
-        reinterpret_cast<uint32_t*>(o)[1] = w1;
-        reinterpret_cast<uint32_t*>(o)[2] = w2;
+      if (x + 8 <= J.out_w && (((uintptr_t)o) & 7u) == 0) {
+        uint32_t w[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {  // bytes 4k .. 4k+3 of R0 G0 B0 R1 G1 B1 ...
+          const int b0 = 4 * k, b1 = b0 + 1, b2 = b0 + 2, b3 = b0 + 3;
+          w[k] = pack4(px[r][b0 / 3][b0 % 3], px[r][b1 / 3][b1 % 3], px[r][b2 / 3][b2 % 3], px[r][b3 / 3][b3 % 3]);
+        }
+        reinterpret_cast<uint2*>(o)[0] = make_uint2(w[0], w[1]);
+        reinterpret_cast<uint2*>(o)[1] = make_uint2(w[2], w[3]);
+        reinterpret_cast<uint2*>(o)[2] = make_uint2(w[4], w[5]);
       } else {
-        for (int i = 0; i < 4 && x + i < J.out_w; i++)
+        for (int i = 0; i < 8 && x + i < J.out_w; i++)
           for (int ch = 0; ch < 3; ch++) o[i * 3 + ch] = (uint8_t)px[r][i][ch];
       }
     }
@@ -77,7 +98,7 @@ __global__ void __launch_bounds__(256) color_stitch_kernel(ColorJob J, Coeffs K,
 #pragma unroll
     for (int r = 0; r < 2; r++) {
       if (r == 1 && !two_rows) break;
-      for (int i = 0; i < 4 && x + i < J.out_w; i++) {
+      for (int i = 0; i < 8 && x + i < J.out_w; i++) {
         const uint32_t sx = x + i, sy = y + r;
         uint32_t dx, dy;
         if (J.rotation == 1) {
@@ -116,9 +137,10 @@ cudaError_t launch_color(const ColorJob& job, cudaStream_t stream) {
     if (bt709) k.rv = 459, k.gu = -55, k.gv = -136, k.bu = 541;
     else k.rv = 409, k.gu = -100, k.gv = -208, k.bu = 516;
   }
-  const uint32_t groups = (job.out_w + 3) / 4;
+  const uint32_t groups = (job.out_w + 7) / 8;
   const uint32_t xblocks = (groups + 255) / 256, row_pairs = (job.out_h + 1) / 2;
-  color_stitch_kernel<<<job.n_images * row_pairs * xblocks, 256, 0, stream>>>(job, k, row_pairs, xblocks);
+  if (job.full_range) color_stitch_kernel<true><<<job.n_images * row_pairs * xblocks, 256, 0, stream>>>(job, k, row_pairs, xblocks);
+  else color_stitch_kernel<false><<<job.n_images * row_pairs * xblocks, 256, 0, stream>>>(job, k, row_pairs, xblocks);
   return cudaGetLastError();
 }
 

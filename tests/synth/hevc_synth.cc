@@ -98,14 +98,14 @@ struct EncEngine {
   }
   void encode_decision(const CabacTabs* T, uint32_t& s, int bin) {
     const uint32_t q = (range >> 6) & 3u;
-    const uint32_t lps = (T->st_lps[s] >> (q << 3)) & 0xffu;
+    const uint32_t lps = (T->st[s].lps >> (q << 3)) & 0xffu;
     range -= lps;
     if (bin != (int)(s & 1u)) {
       low += range;
       range = lps;
-      s = (T->st_next[s] >> 8) & 0xffu;
+      s = (T->st[s].next >> 8) & 0xffu;
     } else {
-      s = T->st_next[s] & 0xffu;
+      s = T->st[s].next & 0xffu;
     }
     renorm();
   }
