@@ -113,6 +113,8 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   P.T = &sh->tabs;
   P.ctx = ctx_all + (size_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0 : lane);
   P.ctx_off = (uint32_t)(P.ctx - smem_raw);
+  // keep the table offset in a register: left alone, ptxas rematerialises it from %tid (S2R + 6 ALU ops) at every bin
+  asm volatile("" : "+r"(P.ctx_off));
   P.pp = pp;
   P.tp = tp;
   P.tu_map = A.tu_map + tp->tu_off;

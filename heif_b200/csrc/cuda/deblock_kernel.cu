@@ -201,26 +201,28 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
   }
 }
 
-// grid: flat over (tile, cell row of the three stacked planes, block of cell columns)
-__global__ void __launch_bounds__(128) deblock_kernel(Arenas A, uint32_t rows, uint32_t xblocks) {
-  const uint32_t per_tile = rows * xblocks;
-  const uint32_t tile = blockIdx.x / per_tile, rem = blockIdx.x % per_tile;
+// grid: flat over (tile, block of cells of the tile); the cells of the three planes are numbered consecutively, row by row
+__global__ void __launch_bounds__(128, 6) deblock_kernel(Arenas A, uint32_t blocks_per_tile) {
+  const uint32_t tile = blockIdx.x / blocks_per_tile;
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0 || tp->deblock_disabled) return;
-  const int k = (int)((rem % xblocks) * blockDim.x + threadIdx.x);
-  int j = (int)(rem / xblocks);
-  const int rows_y = (pp->h >> 3) + 1, rows_c = pp->chroma ? (((pp->h >> 1) + 7) >> 3) + 1 : 0;
+  uint32_t g = (blockIdx.x % blocks_per_tile) * blockDim.x + threadIdx.x;
+  const uint32_t cx_y = (uint32_t)(pp->w >> 3) + 1, cy_y = (uint32_t)(pp->h >> 3) + 1;
+  const uint32_t cx_c = (uint32_t)(((pp->w >> 1) + 7) >> 3) + 1, cy_c = (uint32_t)(((pp->h >> 1) + 7) >> 3) + 1;
+  const uint32_t n_y = cx_y * cy_y, n_c = pp->chroma ? cx_c * cy_c : 0u;
   int cidx = 0;
-  if (j >= rows_y) {
-    j -= rows_y;
+  if (g >= n_y) {
+    g -= n_y;
     cidx = 1;
-    if (j >= rows_c) {
-      j -= rows_c;
+    if (g >= n_c) {
+      g -= n_c;
       cidx = 2;
-      if (j >= rows_c) return;
+      if (g >= n_c) return;
     }
   }
+  const uint32_t cpr = cidx ? cx_c : cx_y;
+  const int k = (int)(g % cpr), j = (int)(g / cpr);
   Pic pic;
   pic.tu_map = A.tu_map + tp->tu_off;
   pic.qp_map = A.qp_map + tp->map8_off;
@@ -229,11 +231,9 @@ __global__ void __launch_bounds__(128) deblock_kernel(Arenas A, uint32_t rows, u
   pic.wctb = pp->wctb;
   const int beta_off2 = tp->beta_offset_div2 * 2, tc_off2 = tp->tc_offset_div2 * 2;
   if (cidx == 0) {
-    if (k > (pp->w >> 3)) return;
     deblock_cell<0>(pic, A.recon + tp->plane_off[0], pp->pitch_y, pp->w, pp->h, k, j, beta_off2, tc_off2, 0);
   } else {
     const int pw = pp->w >> 1, ph = pp->h >> 1;
-    if (k > ((pw + 7) >> 3)) return;
     if (8 * k - 4 >= pw || 8 * j - 4 >= ph) return;
     deblock_cell<1>(pic, A.recon + tp->plane_off[cidx], pp->pitch_c, pw, ph, k, j, beta_off2, tc_off2,
                     cidx == 1 ? pp->pps_cb_qp_offset : pp->pps_cr_qp_offset);
@@ -244,10 +244,9 @@ __global__ void __launch_bounds__(128) deblock_kernel(Arenas A, uint32_t rows, u
 
 cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const uint32_t cells_x = (max_w >> 3) + 1;
-  const uint32_t rows = ((max_h >> 3) + 1) + 2 * ((((max_h >> 1) + 7) >> 3) + 1);
-  const uint32_t xblocks = (cells_x + 127) / 128;
-  deblock_kernel<<<A.n_tiles * rows * xblocks, 128, 0, stream>>>(A, rows, xblocks);
+  const uint32_t cells = ((max_w >> 3) + 1) * ((max_h >> 3) + 1) + 2 * ((((max_w >> 1) + 7) >> 3) + 1) * ((((max_h >> 1) + 7) >> 3) + 1);
+  const uint32_t bpt = (cells + 127) / 128;
+  deblock_kernel<<<A.n_tiles * bpt, 128, 0, stream>>>(A, bpt);
   return cudaGetLastError();
 }
 

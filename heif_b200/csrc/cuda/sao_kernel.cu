@@ -1,5 +1,5 @@
 // Stage 5: sample adaptive offset (H.265 8.7.3): deblocked picture (recon arena) -> final arena.
-// Absent from the reference (slice.rs:249-251 is todo!()).  Purely bandwidth bound: a thread produces four
+// Absent from the reference (slice.rs:249-251 is todo!()).  A thread produces eight
 // horizontally adjacent samples from at most three rows of the deblocked picture; the rows above and below
 // come out of L1/L2 because neighbouring threads just fetched them.
 #include <cuda_runtime.h>
@@ -14,36 +14,50 @@ namespace {
 __device__ __forceinline__ int clip8(int v) { return min(255, max(0, v)); }
 __device__ __forceinline__ int sgn(int v) { return (v > 0) - (v < 0); }
 
-// bytes x-1 .. x+4 of a row as a 48-bit window (missing neighbours read as 0; callers mask them out)
-__device__ __forceinline__ uint64_t row_window(const uint8_t* row, int x, int pw) {
-  const uint32_t c = *reinterpret_cast<const uint32_t*>(row + x);
+// A thread produces eight horizontally adjacent samples.  Rows are fetched as 8-byte words plus the two bytes beside
+// them; sample i of the thread sits at byte i + 1 of the 10-byte window (lo = bytes 0..7, hi = bytes 8..9).
+struct Window {
+  uint64_t lo;
+  uint32_t hi;
+  __device__ __forceinline__ int at(int i) const { return i < 8 ? (int)((lo >> (8 * i)) & 0xffu) : (int)((hi >> (8 * (i - 8))) & 0xffu); }
+};
+__device__ __forceinline__ Window row_window(const uint8_t* row, int x, int pw) {
+  const uint2 c = *reinterpret_cast<const uint2*>(row + x);
+  const uint64_t c64 = ((uint64_t)c.y << 32) | c.x;
   const uint32_t l = x > 0 ? row[x - 1] : 0u;
-  const uint32_t r = x + 4 < pw ? row[x + 4] : 0u;
-  return (uint64_t)l | ((uint64_t)c << 8) | ((uint64_t)r << 40);
+  const uint32_t r = x + 8 < pw ? row[x + 8] : 0u;
+  Window w;
+  w.lo = (c64 << 8) | l;
+  w.hi = (uint32_t)(c64 >> 56) | (r << 8);
+  return w;
 }
 
-// grid: flat over (tile, row of the three stacked planes, block of 4-sample groups)
-__global__ void __launch_bounds__(128) sao_kernel(Arenas A, uint32_t rows, uint32_t xblocks) {
-  const uint32_t per_tile = rows * xblocks;
-  const uint32_t tile = blockIdx.x / per_tile, rem = blockIdx.x % per_tile;
+// grid: flat over (tile, block of 8-sample groups of the tile); the groups of the three planes are numbered consecutively, row
+// by row, so CTAs stay full whatever the picture width is
+__global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_tile) {
+  const uint32_t tile = blockIdx.x / blocks_per_tile;
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0) return;
-  int y = (int)(rem / xblocks), cidx = 0;
-  if (y >= pp->h) {
-    if (!pp->chroma) return;
-    y -= pp->h;
+  uint32_t g = (blockIdx.x % blocks_per_tile) * blockDim.x + threadIdx.x;
+  const uint32_t gy = (uint32_t)(pp->w + 7) >> 3, gc = (uint32_t)((pp->w >> 1) + 7) >> 3;  // groups per row
+  const uint32_t n_y = gy * (uint32_t)pp->h, n_c = pp->chroma ? gc * (uint32_t)(pp->h >> 1) : 0u;
+  int cidx = 0;
+  if (g >= n_y) {
+    g -= n_y;
     cidx = 1;
-    if (y >= (pp->h >> 1)) {
-      y -= pp->h >> 1;
+    if (g >= n_c) {
+      g -= n_c;
       cidx = 2;
-      if (y >= (pp->h >> 1)) return;
+      if (g >= n_c) return;
     }
   }
+  const uint32_t gpr = cidx ? gc : gy;
+  const int y = (int)(g / gpr);
   const int sub = cidx ? 1 : 0;
   const int pw = pp->w >> sub, ph = pp->h >> sub, pitch = cidx ? pp->pitch_c : pp->pitch_y;
-  const int x = (int)((rem % xblocks) * blockDim.x + threadIdx.x) * 4;
-  if (x >= pw) return;
+  const int x = (int)(g % gpr) * 8;
+  if (x >= pw) return;  // plane widths are multiples of 4; pitches of 64, so the 8-byte access below stays inside the row
   const uint8_t* src = A.recon + tp->plane_off[cidx];
   uint8_t* dst = A.final_ + tp->plane_off[cidx];
   const uint8_t* row = src + (size_t)y * pitch;
@@ -51,56 +65,68 @@ __global__ void __launch_bounds__(128) sao_kernel(Arenas A, uint32_t rows, uint3
   const uint32_t word = A.sao[tp->sao_off + (size_t)((y >> log2_cs) * pp->wctb + (x >> log2_cs)) * 4 + cidx];
   const bool enabled = cidx == 0 ? tp->sao_luma : tp->sao_chroma;
   const int type = enabled ? (int)(word & 3u) : 0;
-  const uint32_t center = *reinterpret_cast<const uint32_t*>(row + x);
-  uint32_t out = center;
+  const uint2 center = *reinterpret_cast<const uint2*>(row + x);
+  uint32_t out[2] = {center.x, center.y};
   if (type) {
-    int off[5];
-    off[0] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++) off[k + 1] = (int)(((word >> (8 + 4 * k)) & 15u) ^ 8u) - 8;
+    // the four offsets as one word of signed nibbles; entry 0 of the edge table (edgeIdx 2 -> 0) is zero
+    const uint32_t offs = (word >> 8) & 0xffffu;
     if (type == 1) {  // band offset
       const int band_pos = (int)((word >> 2) & 31u);
-      out = 0;
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        int v = (int)((center >> (8 * i)) & 0xffu);
-        const int k = ((v >> 3) - band_pos) & 31;
-        if (k < 4) v = clip8(v + (k == 0 ? off[1] : k == 1 ? off[2] : k == 2 ? off[3] : off[4]));
-        out |= (uint32_t)v << (8 * i);
+      for (int h = 0; h < 2; h++) {
+        uint32_t o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          int v = (int)((out[h] >> (8 * i)) & 0xffu);
+          const int k = ((v >> 3) - band_pos) & 31;
+          if (k < 4) v = clip8(v + ((int)(offs << (28 - 4 * k)) >> 28));
+          o |= (uint32_t)v << (8 * i);
+        }
+        out[h] = o;
       }
     } else {  // edge offset
       const int cl = (int)((word >> 2) & 3u);
       const int dxa = cl == 1 ? 0 : (cl == 3 ? 1 : -1), dya = cl == 0 ? 0 : -1;  // b is the mirror of a
       const bool rows_ok = dya == 0 || (y > 0 && y + 1 < ph);
       if (rows_ok) {
-        const uint64_t wa = row_window(row + (ptrdiff_t)dya * pitch, x, pw);
-        const uint64_t wb = row_window(row - (ptrdiff_t)dya * pitch, x, pw);
-        out = 0;
+        const Window wa = row_window(row + (ptrdiff_t)dya * pitch, x, pw);
+        const Window wb = row_window(row - (ptrdiff_t)dya * pitch, x, pw);
+        // edgeIdx = 2 + sign(v - a) + sign(v - b) -> offset index {1, 2, 0, 3, 4}: nibble table, 4 bits per edgeIdx
+        const uint32_t table = (offs & 0xfu) | (((offs >> 4) & 0xfu) << 4) | (((offs >> 8) & 0xfu) << 12) | (((offs >> 12) & 0xfu) << 16);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          int v = (int)((center >> (8 * i)) & 0xffu);
-          const int xa = x + i + dxa, xb = x + i - dxa;
-          if (xa >= 0 && xa < pw && xb >= 0 && xb < pw) {
-            const int a = (int)((wa >> (8 * (i + 1 + dxa))) & 0xffu);
-            const int b = (int)((wb >> (8 * (i + 1 - dxa))) & 0xffu);
-            const int e = 2 + sgn(v - a) + sgn(v - b);
-            const int o = e == 0 ? off[1] : e == 1 ? off[2] : e == 2 ? 0 : e == 3 ? off[3] : off[4];
-            v = clip8(v + o);
+        for (int h = 0; h < 2; h++) {
+          uint32_t o = 0;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; i4++) {
+            const int i = 4 * h + i4;
+            int v = (int)((out[h] >> (8 * i4)) & 0xffu);
+            const int xa = x + i + dxa, xb = x + i - dxa;
+            if (x + i < pw && xa >= 0 && xa < pw && xb >= 0 && xb < pw) {
+              const int a = wa.at(i + 1 + dxa), b = wb.at(i + 1 - dxa);
+              const int e = 2 + sgn(v - a) + sgn(v - b);
+              v = clip8(v + ((int)(table << (28 - 4 * e)) >> 28));
+            }
+            o |= (uint32_t)v << (8 * i4);
           }
-          out |= (uint32_t)v << (8 * i);
+          out[h] = o;
         }
       }
     }
   }
-  *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x) = out;
+  if (x + 8 <= pw) {
+    *reinterpret_cast<uint2*>(dst + (size_t)y * pitch + x) = make_uint2(out[0], out[1]);
+  } else {
+    *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x) = out[0];
+  }
 }
 
 }  // namespace
 
 cudaError_t launch_sao(const Arenas& A, uint32_t max_pitch, uint32_t max_h, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const uint32_t xblocks = (max_pitch / 4 + 127) / 128, rows = max_h * 2;
-  sao_kernel<<<A.n_tiles * rows * xblocks, 128, 0, stream>>>(A, rows, xblocks);
+  const uint32_t groups = ((max_pitch + 7) / 8) * max_h * 2;  // upper bound on the 8-sample groups of a tile
+  const uint32_t bpt = (groups + 255) / 256;
+  sao_kernel<<<A.n_tiles * bpt, 256, 0, stream>>>(A, bpt);
   return cudaGetLastError();
 }
 
