@@ -198,9 +198,12 @@ __device__ __forceinline__ void predict_block(const Ctu& c, int cidx, uint8_t* b
   __syncwarp();
 }
 
-__global__ void __launch_bounds__(256, 3) intra_kernel(Arenas A, int n_slots, int warp_bytes, int log2_ctb_alloc) {
+#ifndef HEIC_INTRA_MIN_CTAS
+#define HEIC_INTRA_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, int warp_bytes, int log2_ctb_alloc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = order[blockIdx.x];
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0) return;
@@ -376,7 +379,7 @@ int intra_warp_bytes(int log2_ctb) {
 
 }  // namespace
 
-cudaError_t launch_intra(const Arenas& A, int max_log2_ctb, int max_hctb, int n_slots, cudaStream_t stream) {
+cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
   const int wb = intra_warp_bytes(max_log2_ctb);
   const size_t smem = (n_slots > 1 ? (((size_t)max_hctb * 4 + 15) & ~(size_t)15) : 0) + (size_t)n_slots * wb;
@@ -386,7 +389,7 @@ cudaError_t launch_intra(const Arenas& A, int max_log2_ctb, int max_hctb, int n_
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, n_slots, wb, max_log2_ctb);
+  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, wb, max_log2_ctb);
   return cudaGetLastError();
 }
 

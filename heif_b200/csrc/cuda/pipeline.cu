@@ -120,7 +120,7 @@ struct heic_b200_batch {
   std::vector<ScalingSet> scaling;
   std::vector<TileParams> tiles;
   std::vector<ImageInfo> images;
-  std::vector<uint32_t> substreams, order;
+  std::vector<uint32_t> substreams, order, heavy_first;
   std::vector<CabacClass> classes;
   size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0, wpp_bytes = 0;
   size_t rgb_pitch = 0, rgb_image_stride = 0;
@@ -128,7 +128,7 @@ struct heic_b200_batch {
   int max_log2_ctb = 4, max_log2_tb = 2, intra_slots = 1, max_hctb = 1;
   uint32_t stages_run = 0;
   PinnedBuf h_bitstream, h_status, h_params;
-  size_t off_sub = 0, off_order = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
+  size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
   DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
       d_qp, d_sao, d_wpp, d_status, d_rgb;
   Arenas arenas() const {
@@ -173,6 +173,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   images.clear();
   substreams.clear();
   order.clear();
+  heavy_first.clear();
   classes.clear();
   bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = wpp_bytes = 0;
   max_tu = max_w = max_h = max_pitch = 0;
@@ -312,6 +313,12 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     classes.push_back(c);
   }
 
+  // every tile once, largest slice first: launch order of the one-CTA-per-picture intra kernel (the heaviest pictures
+  // must not be the last ones to start)
+  heavy_first.resize(tiles.size());
+  for (uint32_t t = 0; t < tiles.size(); t++) heavy_first[t] = t;
+  std::stable_sort(heavy_first.begin(), heavy_first.end(), [&](uint32_t a, uint32_t b) { return tiles[a].bs_len > tiles[b].bs_len; });
+
   // ---- device memory + uploads: one pinned blob for all parameter tables, one for the slice data ------------------
   cudaStream_t st = stream;
   h_bitstream.ensure(bs_bytes + 16);
@@ -328,7 +335,8 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   }
   off_sub = 0;
   off_order = up(off_sub + substreams.size() * 4, 256);
-  off_pics = up(off_order + order.size() * 4, 256);
+  off_heavy = up(off_order + order.size() * 4, 256);
+  off_pics = up(off_heavy + heavy_first.size() * 4, 256);
   off_tiles = up(off_pics + pics.size() * sizeof(PicParams), 256);
   off_scaling = up(off_tiles + tiles.size() * sizeof(TileParams), 256);
   const size_t params_bytes = up(off_scaling + scaling.size() * sizeof(ScalingSet), 256);
@@ -337,6 +345,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     uint8_t* hp = (uint8_t*)h_params.p;
     std::memcpy(hp + off_sub, substreams.data(), substreams.size() * 4);
     std::memcpy(hp + off_order, order.data(), order.size() * 4);
+    std::memcpy(hp + off_heavy, heavy_first.data(), heavy_first.size() * 4);
     std::memcpy(hp + off_pics, pics.data(), pics.size() * sizeof(PicParams));
     std::memcpy(hp + off_tiles, tiles.data(), tiles.size() * sizeof(TileParams));
     std::memcpy(hp + off_scaling, scaling.data(), scaling.size() * sizeof(ScalingSet));
@@ -384,7 +393,7 @@ void heic_b200_batch::run(uint32_t mask) {
     // enough pictures to fill the GPU with one warp each: drop the intra-picture wavefront (no waiting at all)
     int slots = tiles.size() >= (size_t)ctx->intra_single_warp_tiles ? 1 : intra_slots;
     if (ctx->intra_slots > 0) slots = std::min(ctx->intra_slots, std::max(1, max_hctb));
-    CU(launch_intra(A, max_log2_ctb, max_hctb, slots, st));
+    CU(launch_intra(A, (const uint32_t*)((const uint8_t*)d_params.p + off_heavy), max_log2_ctb, max_hctb, slots, st));
     ctx->launches++;
   }
   if (mask & HEIC_STAGE_DEBLOCK) {
