@@ -131,6 +131,24 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
     // ---- scaling + first (column) pass -------------------------------------------------------
     int x[N], y[N];
     int nz_rows = 0;
+    // raw levels first: only the rows up to the last non-zero one (warp-uniform bound) are scaled afterwards
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      x[j] = active ? (int)blk[j * N + col] : 0;
+      nz_rows = x[j] ? j + 1 : nz_rows;
+    }
+    // extents of the non-zero coefficients, uniform over the warp so the butterfly variant is too
+    int nz1 = nz_rows;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) nz1 = max(nz1, __shfl_xor_sync(0xffffffffu, nz1, o));
+    const uint32_t col_mask = __ballot_sync(0xffffffffu, nz_rows > 0);
+    // highest non-zero column index + 1 within any block of the batch
+    int nz2 = 0;
+#pragma unroll
+    for (int g = 0; g < K; g++) {
+      uint32_t mg = (col_mask >> (g * N)) & (N == 32 ? 0xffffffffu : ((1u << N) - 1u));
+      nz2 = max(nz2, 32 - __clz(mg));
+    }
     if (active) {
       int qp = (int)tu_qp(w);
       if (CIDX) {
@@ -146,28 +164,20 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
       constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
 #pragma unroll
       for (int j = 0; j < N; j++) {
-        const int lvl = blk[j * N + col];
-        const int mm = m ? (int)m[j * N + col] : 16;
-        long long p = (long long)lvl * (mm * scale) + (1ll << (BD_SHIFT - 1));
-        p >>= BD_SHIFT;
-        x[j] = (int)min(32767ll, max(-32768ll, p));
-        nz_rows = lvl ? j + 1 : nz_rows;
+        if (j < nz1) {  // warp-uniform
+          const int lvl = x[j];
+          const int ms = (m ? (int)m[j * N + col] : 16) * scale;  // <= 255 * (72 << 8) < 2^23
+          int v;
+          if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: the product fits 32 bits (the common case by far)
+            v = (lvl * ms + (1 << (BD_SHIFT - 1))) >> BD_SHIFT;
+          } else {
+            long long p = (long long)lvl * ms + (1ll << (BD_SHIFT - 1));
+            p >>= BD_SHIFT;
+            v = (int)min(32767ll, max(-32768ll, p));
+          }
+          x[j] = min(32767, max(-32768, v));
+        }
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < N; j++) x[j] = 0;
-    }
-    // extents of the non-zero coefficients, uniform over the warp so the butterfly variant is too
-    int nz1 = nz_rows;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) nz1 = max(nz1, __shfl_xor_sync(0xffffffffu, nz1, o));
-    const uint32_t col_mask = __ballot_sync(0xffffffffu, nz_rows > 0);
-    // highest non-zero column index + 1 within any block of the batch
-    int nz2 = 0;
-#pragma unroll
-    for (int g = 0; g < K; g++) {
-      uint32_t mg = (col_mask >> (g * N)) & (N == 32 ? 0xffffffffu : ((1u << N) - 1u));
-      nz2 = max(nz2, 32 - __clz(mg));
     }
     if (tskip) {
 #pragma unroll
@@ -228,6 +238,7 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
 }
 
 constexpr int kWarpsPerCta = 8;
+constexpr uint32_t kRegionsPerCta = 64;
 constexpr int kTmpPerWarp = 32 * 34;  // int16 elements: one 32x32 block with padded rows
 
 // ---- n >= 8: one launch per (CIDX kind, N) ------------------------------------------------------------------
@@ -241,21 +252,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A) 
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0) return;
   if (KIND == 1 && !pp->chroma) return;
-  const uint32_t region = blockIdx.y * kWarpsPerCta + warp;
-  if (region * 64 >= (uint32_t)pp->n_tu) return;
   WarpCtx c;
   c.pp = pp;
   c.tp = tp;
   c.sc = A.scaling + pp->scaling_set;
   c.tmp = tmp_all[warp];
   c.lane = lane;
-  c.tu = A.tu_map + tp->tu_off + (size_t)region * 64;
-  c.n_entries = min(64, pp->n_tu - (int)region * 64);
-  if (KIND == 0) {
-    run_size<N, 0>(c, A.coeff + tp->coeff_off[0] + (size_t)region * 1024);
-  } else {
-    run_size<N, 1>(c, A.coeff + tp->coeff_off[1] + (size_t)region * 256);
-    run_size<N, 2>(c, A.coeff + tp->coeff_off[2] + (size_t)region * 256);
+  // a CTA sweeps kRegionsPerCta consecutive regions, one per warp at a time (fewer, longer-lived CTAs)
+  const uint32_t r_end = min((blockIdx.y + 1) * kRegionsPerCta, ((uint32_t)pp->n_tu + 63u) / 64u);
+  for (uint32_t region = blockIdx.y * kRegionsPerCta + warp; region < r_end; region += kWarpsPerCta) {
+    c.tu = A.tu_map + tp->tu_off + (size_t)region * 64;
+    c.n_entries = min(64, pp->n_tu - (int)region * 64);
+    if (KIND == 0) {
+      run_size<N, 0>(c, A.coeff + tp->coeff_off[0] + (size_t)region * 1024);
+    } else {
+      run_size<N, 1>(c, A.coeff + tp->coeff_off[1] + (size_t)region * 256);
+      run_size<N, 2>(c, A.coeff + tp->coeff_off[2] + (size_t)region * 256);
+    }
   }
 }
 
@@ -289,10 +302,15 @@ __device__ __forceinline__ void block4(int16_t* blk, uint32_t w, const PicParams
 #pragma unroll
   for (int i = 0; i < 16; i++) {
     const int lvl = (int)(int16_t)((raw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-    const int mm = (int)((mraw[i >> 2] >> (8 * (i & 3))) & 0xffu);
-    long long p = (long long)lvl * (mm * scale) + 16;  // bdShift = 5 for 4x4, 8-bit
-    p >>= 5;
-    d[i] = (int)min(32767ll, max(-32768ll, p));
+    const int ms = (int)((mraw[i >> 2] >> (8 * (i & 3))) & 0xffu) * scale;
+    int v;
+    if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: 32-bit product (bdShift = 5 for 4x4, 8-bit)
+      v = (lvl * ms + 16) >> 5;
+    } else {
+      long long p = ((long long)lvl * ms + 16) >> 5;
+      v = (int)min(32767ll, max(-32768ll, p));
+    }
+    d[i] = min(32767, max(-32768, v));
   }
   int out[16];
   if (tu_tskip(w, CIDX)) {
@@ -365,7 +383,7 @@ __global__ void __launch_bounds__(256) transform4_kernel(Arenas A) {
 cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
   const uint32_t regions = (max_tu_per_tile + 63u) / 64u;
-  const dim3 grid(A.n_tiles, (regions + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
+  const dim3 grid(A.n_tiles, (regions + kRegionsPerCta - 1) / kRegionsPerCta), block(kWarpsPerCta * 32);
   if (max_log2_tb >= 5) {
     transform_kernel<32, 0><<<grid, block, 0, stream>>>(A);
     transform_kernel<16, 1><<<grid, block, 0, stream>>>(A);
