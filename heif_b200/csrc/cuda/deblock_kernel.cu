@@ -201,28 +201,27 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
   }
 }
 
-// grid: flat over (tile, block of cells of the tile); the cells of the three planes are numbered consecutively, row by row
+// One launch for luma (KIND 0) and one for the two chroma planes (KIND 1): each launch then runs a single filter body
+// that fits the instruction cache.  grid: flat over (tile, block of cells of the tile), cells numbered row by row.
+template <int KIND>
 __global__ void __launch_bounds__(128, 6) deblock_kernel(Arenas A, uint32_t blocks_per_tile) {
   const uint32_t tile = blockIdx.x / blocks_per_tile;
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
   if (A.status[tile].code != 0 || tp->deblock_disabled) return;
+  if (KIND == 1 && !pp->chroma) return;
   uint32_t g = (blockIdx.x % blocks_per_tile) * blockDim.x + threadIdx.x;
-  const uint32_t cx_y = (uint32_t)(pp->w >> 3) + 1, cy_y = (uint32_t)(pp->h >> 3) + 1;
-  const uint32_t cx_c = (uint32_t)(((pp->w >> 1) + 7) >> 3) + 1, cy_c = (uint32_t)(((pp->h >> 1) + 7) >> 3) + 1;
-  const uint32_t n_y = cx_y * cy_y, n_c = pp->chroma ? cx_c * cy_c : 0u;
-  int cidx = 0;
-  if (g >= n_y) {
-    g -= n_y;
-    cidx = 1;
-    if (g >= n_c) {
-      g -= n_c;
-      cidx = 2;
-      if (g >= n_c) return;
-    }
+  const int pw = pp->w >> KIND, ph = pp->h >> KIND;
+  const uint32_t cx = (uint32_t)((pw + 7) >> 3) + 1, cy = (uint32_t)((ph + 7) >> 3) + 1;
+  int cidx = KIND;
+  if (g >= cx * cy) {
+    if (KIND == 0) return;
+    g -= cx * cy;
+    cidx = 2;
+    if (g >= cx * cy) return;
   }
-  const uint32_t cpr = cidx ? cx_c : cx_y;
-  const int k = (int)(g % cpr), j = (int)(g / cpr);
+  const int k = (int)(g % cx), j = (int)(g / cx);
+  if (8 * k - 4 >= pw || 8 * j - 4 >= ph) return;
   Pic pic;
   pic.tu_map = A.tu_map + tp->tu_off;
   pic.qp_map = A.qp_map + tp->map8_off;
@@ -230,23 +229,19 @@ __global__ void __launch_bounds__(128, 6) deblock_kernel(Arenas A, uint32_t bloc
   pic.log2_ctb = pp->log2_ctb;
   pic.wctb = pp->wctb;
   const int beta_off2 = tp->beta_offset_div2 * 2, tc_off2 = tp->tc_offset_div2 * 2;
-  if (cidx == 0) {
-    deblock_cell<0>(pic, A.recon + tp->plane_off[0], pp->pitch_y, pp->w, pp->h, k, j, beta_off2, tc_off2, 0);
-  } else {
-    const int pw = pp->w >> 1, ph = pp->h >> 1;
-    if (8 * k - 4 >= pw || 8 * j - 4 >= ph) return;
-    deblock_cell<1>(pic, A.recon + tp->plane_off[cidx], pp->pitch_c, pw, ph, k, j, beta_off2, tc_off2,
-                    cidx == 1 ? pp->pps_cb_qp_offset : pp->pps_cr_qp_offset);
-  }
+  deblock_cell<KIND>(pic, A.recon + tp->plane_off[cidx], KIND ? pp->pitch_c : pp->pitch_y, pw, ph, k, j, beta_off2, tc_off2,
+                     cidx == 0 ? 0 : (cidx == 1 ? pp->pps_cb_qp_offset : pp->pps_cr_qp_offset));
 }
 
 }  // namespace
 
 cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const uint32_t cells = ((max_w >> 3) + 1) * ((max_h >> 3) + 1) + 2 * ((((max_w >> 1) + 7) >> 3) + 1) * ((((max_h >> 1) + 7) >> 3) + 1);
-  const uint32_t bpt = (cells + 127) / 128;
-  deblock_kernel<<<A.n_tiles * bpt, 128, 0, stream>>>(A, bpt);
+  const uint32_t cells_y = (((max_w + 7) >> 3) + 1) * (((max_h + 7) >> 3) + 1);
+  const uint32_t cells_c = 2 * ((((max_w >> 1) + 7) >> 3) + 1) * ((((max_h >> 1) + 7) >> 3) + 1);
+  const uint32_t by = (cells_y + 127) / 128, bc = (cells_c + 127) / 128;
+  deblock_kernel<0><<<A.n_tiles * by, 128, 0, stream>>>(A, by);
+  deblock_kernel<1><<<A.n_tiles * bc, 128, 0, stream>>>(A, bc);
   return cudaGetLastError();
 }
 

@@ -398,7 +398,7 @@ void heic_b200_batch::run(uint32_t mask) {
   }
   if (mask & HEIC_STAGE_DEBLOCK) {
     CU(launch_deblock(A, max_w, max_h, st));
-    ctx->launches++;
+    ctx->launches += 2;  // luma + chroma
   }
   if (mask & HEIC_STAGE_SAO) {
     CU(launch_sao(A, max_pitch, max_h, st));
