@@ -118,10 +118,43 @@ def cpu_decode_images(heic_file, n_images: int, threads: int) -> float:
     t0 = time.perf_counter()
     with ThreadPoolExecutor(threads) as ex:
         planes = list(ex.map(one, range(n_images * img.n_tiles)))
-        per_image = [np.concatenate(planes[i * img.n_tiles:(i + 1) * img.n_tiles]) for i in range(n_images)]
-        list(ex.map(lambda p: oracle_py.color_stitch(p, img.grid_rows, img.grid_cols, w, h, img.output_width, img.output_height,
-                                                     img.sps.video_full_range_flag, img.sps.matrix_coeffs), per_image))
+        # colour + stitch one grid row per task (the last row is cropped by the canvas height)
+        jobs = []
+        for i in range(n_images):
+            for r in range(img.grid_rows):
+                row = np.concatenate(planes[i * img.n_tiles + r * img.grid_cols:i * img.n_tiles + (r + 1) * img.grid_cols])
+                jobs.append((row, min(h, img.output_height - r * h)))
+        list(ex.map(lambda j: oracle_py.color_stitch(j[0], 1, img.grid_cols, w, h, img.output_width, j[1],
+                                                     img.sps.video_full_range_flag, img.sps.matrix_coeffs), jobs))
     return time.perf_counter() - t0
+
+
+def ffmpeg_decode_images(heic_file, n_images: int, threads: int):
+    """FFmpeg's native HEVC decoder (planes only, no colour conversion) on the same tiles, one decoder per thread.
+    Extra context next to the oracle port: 'what a CPU does today'.  Returns seconds, or None when FFmpeg is absent."""
+    try:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from oracle.ffmpeg_oracle import FFmpegHevc, annexb
+    except Exception:
+        return None
+    try:
+        ps = [heic_file.parameter_set_nal(t) for t in (32, 33, 34)]
+        aus = [annexb(ps + [heic_file.tile_nal(t)]) for t in range(heic_file.primary.n_tiles)]
+        local = threading.local()
+
+        def one(i):
+            if not hasattr(local, "dec"):
+                local.dec = FFmpegHevc()
+            local.dec.decode_picture(aus[i % len(aus)])
+
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(threads)))  # warm up: one decoder per thread
+            t0 = time.perf_counter()
+            list(ex.map(one, range(n_images * len(aus))))
+            return time.perf_counter() - t0
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -142,7 +175,7 @@ def run_reference(args):
         cpu_decode_images(f, n_img, cores)
     dt = time.perf_counter() - t0
     value = args.steps * n_img * MP_PER_IMAGE / dt
-    sample = f"{n_img} image(s) = {48 * n_img} real 512x512 tiles of halfmoonbay.heic per step, oracle port (C, -O2), {cores} threads"
+    sample = f"{n_img} image(s) = {48 * n_img} real 512x512 tiles of halfmoonbay.heic per step, oracle port (C, -O3), {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": "decoded MP/s (12MP HEIC grid batch)", "value": round(value, 3), "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
@@ -161,10 +194,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "296")), help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "592")), help="images per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "256")), help="images per reference-facing call")
-    ap.add_argument("--ref-images", type=int, default=2, help="images per step of the CPU arm")
-    ap.add_argument("--cpu-images", type=int, default=4, help="images in the cpu_baseline sample")
+    ap.add_argument("--ref-images", type=int, default=16, help="images per step of the CPU arm")
+    ap.add_argument("--cpu-images", type=int, default=32, help="images in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stages", action="store_true", help="also print a per-stage table to stderr")
     args = ap.parse_args()
@@ -268,11 +301,17 @@ def main():
         stages.append({"kernel": n, "ms": round(stage_ms[n], 4), "alg_GB": round(alg_bytes[n] * n_img / 1e9, 4),
                        "achieved_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
     dom = max(stages, key=lambda s: s["ms"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic_per_image.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture, per image
+        per_image = json.load(open(tpath)).get(dom["kernel"])
+        if per_image:
+            traffic = int(per_image * n_img)
     n_sm = torch.cuda.get_device_properties(local).multi_processor_count
     cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
-    eb = min(args.e2e_batch, args.batch)
+    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, 128), args.batch)  # pinned host RGB: 36.6 MB per image per rank
     out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
@@ -305,7 +344,11 @@ def main():
         cores = os.cpu_count() or 1
         dt = cpu_decode_images(f, args.cpu_images, cores)
         cpu = {"value": round(args.cpu_images * MP_PER_IMAGE / dt, 3), "unit": "MP/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_images} images = {48 * args.cpu_images} real tiles of halfmoonbay.heic, oracle port (C -O2), {cores} threads, {dt:.1f} s"}
+               "sample": f"{args.cpu_images} images = {48 * args.cpu_images} real tiles of halfmoonbay.heic, oracle port (C -O3), {cores} threads, {dt:.1f} s"}
+        fdt = ffmpeg_decode_images(f, args.cpu_images, cores)
+        if fdt:
+            cpu["ffmpeg_hevc"] = {"value": round(args.cpu_images * MP_PER_IMAGE / fdt, 3), "unit": "MP/s", "cores": cores,
+                                  "note": "FFmpeg native hevc decoder, YCbCr planes only (no colour conversion), same tiles; context, not the reference"}
 
     if rank == 0:
         line = {
@@ -318,7 +361,7 @@ def main():
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)",
                        "cabac_tiles_per_cta": int(os.environ.get("HEIC_B200_CABAC_TILES_PER_CTA", "32"))},
             "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                         "frac": dom["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                         "frac": dom["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
                          "note": "dominant kernel by time; CABAC is serial-latency bound (see cabac_bins_per_s_per_sm), per-kernel rooflines in `stages`"},
             "stages": stages,
             "cabac_bins_per_s_per_sm": round(cabac_bins / n_sm, 1), "cabac_bins_per_image": bins_per_step // n_img,
