@@ -316,15 +316,30 @@ def main():
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
     d2h = eb * OUT_H * OUT_W * 3
+    # Double-buffered serving loop over the asynchronous form of the same C-ABI call (heic_b200_decode_grids_submit /
+    # heic_b200_job_wait): call k+1 is submitted before call k is waited for, so its host->device copy and kernels
+    # overlap call k's device->host copy.  Every call carries all of its own copies; two pinned output buffers alternate.
+    out2 = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
+    outs = [out_np, out2.numpy()]
     for _ in range(2):
         dec.decode_grids(images[:eb], out=out_np)
     barrier()
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_steps = max(3, min(args.steps, 6))
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        dec.decode_grids(images[:eb], out=out_np)
+    prev = None
+    for k in range(e2e_steps):
+        job = dec.submit_grids(images[:eb], outs[k & 1])
+        if prev is not None:
+            dec.wait_job(prev)
+        prev = job
+    dec.wait_job(prev)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the plain synchronous call, one at a time, for comparison
+    t0 = time.perf_counter()
+    for _ in range(2):
+        dec.decode_grids(images[:eb], out=out_np)
+    sync_s = (time.perf_counter() - t0) / 2
     e2e_val = eb * MP_PER_IMAGE / e2e_s
 
     # ---- aggregate over ranks: max time --------------------------------------------------------------------
@@ -368,7 +383,9 @@ def main():
             "coded_mp_per_s": round(value * (48 * 512 * 512) / (OUT_W * OUT_H), 2),
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_total, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "images_per_call": eb, "ms_per_call": round(e2e_s * 1e3, 3)},
+                    "images_per_call": eb, "ms_per_call": round(e2e_s * 1e3, 3),
+                    "mode": "double-buffered heic_b200_decode_grids_submit/_job_wait, pinned host RGB",
+                    "synchronous_call_MPps": round(world * eb * MP_PER_IMAGE / sync_s, 2)},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -298,6 +298,22 @@ class HeicDecoder:
         K.check(rc)
         return out
 
+    def submit_grids(self, images, out: np.ndarray, apply_transforms: bool = False):
+        """Asynchronous decode_grids: returns a job; call ``wait_job(job)`` before reading ``out``."""
+        images = list(images)
+        arr = _desc_array(images)
+        n_tiles = sum(im.n_tiles for im in images)
+        st = (K.TileStatus * n_tiles)()
+        job = C.c_void_p()
+        K.check(self._lib.heic_b200_decode_grids_submit(self._h, arr, len(images), out.ctypes.data, out.strides[1], out.strides[0],
+                                                        1 if apply_transforms else 0, st, C.byref(job)))
+        return (job, st, out)
+
+    def wait_job(self, job) -> np.ndarray:
+        h, st, out = job
+        K.check(self._lib.heic_b200_job_wait(h))
+        return out
+
     def decode_grids_yuv(self, images):
         """Batch -> list of (Y, Cb, Cr) planes cropped to the canvas (no colour conversion)."""
         images = list(images)

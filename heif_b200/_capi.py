@@ -158,6 +158,9 @@ SYMBOLS = [
     ("heic_b200_file_info", i32, [_vp, C.POINTER(FileInfo)]),
     ("heic_b200_decode_grids", i32,
      [_vp, C.POINTER(ImageDesc), u32, _vp, _sz, _sz, i32, C.POINTER(TileStatus)]),
+    ("heic_b200_decode_grids_submit", i32,
+     [_vp, C.POINTER(ImageDesc), u32, _vp, _sz, _sz, i32, C.POINTER(TileStatus), C.POINTER(_vp)]),
+    ("heic_b200_job_wait", i32, [_vp]),
     ("heic_b200_decode_grids_yuv", i32,
      [_vp, C.POINTER(ImageDesc), u32, _vp, _vp, _vp, C.POINTER(TileStatus)]),
     ("heic_b200_decode_file", i32, [_vp, C.c_char_p, _sz, _vp, _sz, i32]),

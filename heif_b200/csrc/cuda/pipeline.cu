@@ -81,6 +81,19 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// One submitted decode_grids call: its chunks are in flight on the context's pipeline slots until it is waited for.
+struct heic_b200_job {
+  heic_b200_ctx* ctx = nullptr;
+  heic_tile_status* status = nullptr;     // caller's array, or `local`
+  std::vector<heic_tile_status> local;
+  size_t n_tiles = 0;
+};
+
+struct PipePending {
+  heic_b200_job* job = nullptr;  // null: slot idle
+  size_t tile0 = 0, n_tiles = 0;
+};
+
 struct heic_b200_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -88,16 +101,20 @@ struct heic_b200_ctx {
   uint64_t launches = 0;
   int cabac_tiles_per_cta = 32;  // 32: thread per substream, 1: warp per substream
   int cabac_slots = 0;           // 0: derive from the picture geometry
+  int low_latency_tiles = 384;   // loads of at most this many tiles use the warp-per-substream CABAC mapping
   int cabac_group_factor = 1;    // CABAC CTAs per 32 tiles; > 1 splits heavy groups (measured slower: a CTA costs its
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
-  // decode_grids pipeline: chunks of `pipe_chunk` images rotate over kPipe slots, each with its own stream and
+  // decode_grids pipeline: chunks of `pipe_chunk` images rotate over up to kPipe slots, each with its own stream and
   // scratch batch, so the H2D copy, the kernels and the D2H copy of different chunks overlap
-  static constexpr int kPipe = 4;
+  static constexpr int kPipe = 8;
   int pipe_chunk = 32;
-  cudaStream_t pipe_stream[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+  int pipe_slots = kPipe;
+  cudaStream_t pipe_stream[kPipe] = {};
   std::unique_ptr<heic_b200_batch> pipe_batch[kPipe];
+  PipePending pipe_pending[kPipe];
+  uint32_t pipe_next = 0;  // round-robin slot cursor, continues across calls so that jobs in flight interleave
   ~heic_b200_ctx();
 };
 
@@ -115,6 +132,7 @@ struct CabacClass {  // tiles launched together: same wavefront shape
 struct heic_b200_batch {
   heic_b200_ctx* ctx = nullptr;
   cudaStream_t stream = nullptr;  // ctx->stream for explicit batches, a pipeline stream for decode_grids chunks
+  int tiles_per_cta = 32;         // CABAC mapping of this load: 32 (throughput) or 1 (lowest latency, small loads)
   bool apply_transforms = false;
   std::vector<PicParams> pics;
   std::vector<ScalingSet> scaling;
@@ -182,7 +200,8 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   intra_slots = 1;
   max_hctb = 1;
   stages_run = 0;
-  size_t max_rgb_bytes = 0, max_rgb_pitch = 0;
+  size_t max_rgb_bytes = 0, max_rgb_pitch = 0, n_tiles_hint = 0;
+  for (uint32_t i = 0; i < n_imgs; i++) n_tiles_hint += imgs[i].n_tiles;
   for (uint32_t i = 0; i < n_imgs; i++) {
     const heic_image_desc& im = imgs[i];
     if (!im.tiles || im.n_tiles == 0 || im.n_tiles != im.grid_rows * im.grid_cols)
@@ -267,7 +286,10 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   rgb_image_stride = up(max_rgb_bytes, 256);
 
   // ---- CABAC launch classes: tiles with the same wavefront shape, heaviest first, TILES per CTA ----------
-  const int tpc = ctx->cabac_tiles_per_cta;
+  // few tiles: a warp per substream finishes a 12 MP image in about half the time of the 32-tiles-per-CTA mapping
+  // (the GPU is mostly empty either way); many tiles: thread per substream is 11x the throughput
+  tiles_per_cta = (ctx->cabac_tiles_per_cta == 32 && n_tiles_hint > (size_t)ctx->low_latency_tiles) ? 32 : 1;
+  const int tpc = tiles_per_cta;
   std::map<std::tuple<int, int, int, int>, std::vector<uint32_t>> by_shape;
   for (uint32_t t = 0; t < tiles.size(); t++) {
     const PicParams& pp = pics[tiles[t].pic];
@@ -380,7 +402,7 @@ void heic_b200_batch::run(uint32_t mask) {
     CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
     CU(cudaMemsetAsync(d_sao.p, 0, sao_words * 4, st));  // slices without SAO parse no parameters
     for (const CabacClass& c : classes) {
-      CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, ctx->cabac_tiles_per_cta,
+      CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, tiles_per_cta,
                       c.n_slots, st));
       ctx->launches++;
     }
@@ -496,6 +518,8 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->intra_slots = std::min(8, env_int("HEIC_B200_INTRA_SLOTS", 0));
     c->cabac_group_factor = std::max(1, env_int("HEIC_B200_CABAC_GROUP_FACTOR", 1));
     c->pipe_chunk = std::max(1, env_int("HEIC_B200_PIPE_CHUNK", 32));
+    c->low_latency_tiles = env_int("HEIC_B200_LOW_LATENCY_TILES", 384);
+    c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;
   }));
@@ -636,9 +660,25 @@ int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_
 // The images are processed in chunks that rotate over kPipe (stream, scratch batch) slots: while chunk k's RGB
 // travels to the host, chunk k+1 runs its kernels and chunk k+2's slice data travels to the device.  Output buffers
 // should be pinned host memory; pageable memory works but its copies are staged synchronously.
-static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
-                                 size_t pitch, size_t image_stride, int32_t apply_transforms, uint8_t* y_out,
-                                 uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
+static void harvest_slot(heic_b200_ctx* ctx, int slot) {
+  PipePending& pd = ctx->pipe_pending[slot];
+  if (!pd.job) return;
+  heic_b200_batch* b = ctx->pipe_batch[slot].get();
+  CU(cudaStreamSynchronize(b->stream));
+  const TileStatusDev* s = (const TileStatusDev*)b->h_status.p;
+  heic_tile_status* out = pd.job->status + pd.tile0;
+  for (size_t i = 0; i < pd.n_tiles; i++) {
+    out[i].code = s[i].code;
+    out[i].bins_decoded = s[i].bins;
+    out[i].ctus_decoded = s[i].ctus;
+    out[i].reserved = 0;
+  }
+  pd.job = nullptr;
+}
+
+static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
+                                   size_t pitch, size_t image_stride, int32_t apply_transforms, uint8_t* y_out,
+                                   uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
   if (!ctx || !imgs || !n_imgs) bail(HEIC_E_INVALID_ARG, "null argument");
   CU(cudaSetDevice(ctx->device));
   // validate every descriptor before any work is queued, so a bad image rejects the call as a whole
@@ -657,42 +697,32 @@ static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs
     y_off[i + 1] = y_off[i] + ow * oh;
     c_off[i + 1] = c_off[i] + ((ow + 1) / 2) * ((oh + 1) / 2);
   }
-  std::vector<heic_tile_status> local;
-  heic_tile_status* s_out = status;
-  if (!s_out) {
-    local.resize(first_tile[n_imgs]);
-    s_out = local.data();
+  auto job = std::make_unique<heic_b200_job>();
+  job->ctx = ctx;
+  job->n_tiles = first_tile[n_imgs];
+  job->status = status;
+  if (!job->status) {
+    job->local.resize(job->n_tiles);
+    job->status = job->local.data();
   }
+  // equal chunks (a ramp of small first chunks was measured slower: every chunk pays the CABAC latency floor of its
+  // heaviest tiles while holding a pipeline slot)
   const uint32_t chunk = (uint32_t)std::max(1, ctx->pipe_chunk);
-  const uint32_t n_chunks = (n_imgs + chunk - 1) / chunk;
-  struct Pending {
-    bool busy = false;
-    size_t tile0 = 0, n_tiles = 0;
-  } pending[heic_b200_ctx::kPipe];
-  auto harvest = [&](int slot) {
-    Pending& pd = pending[slot];
-    if (!pd.busy) return;
-    heic_b200_batch* b = ctx->pipe_batch[slot].get();
-    CU(cudaStreamSynchronize(b->stream));
-    const TileStatusDev* s = (const TileStatusDev*)b->h_status.p;
-    for (size_t i = 0; i < pd.n_tiles; i++) {
-      s_out[pd.tile0 + i].code = s[i].code;
-      s_out[pd.tile0 + i].bins_decoded = s[i].bins;
-      s_out[pd.tile0 + i].ctus_decoded = s[i].ctus;
-      s_out[pd.tile0 + i].reserved = 0;
-    }
-    pd.busy = false;
-  };
+  std::vector<uint32_t> chunk_start;
+  for (uint32_t i = 0; i < n_imgs; i += chunk) chunk_start.push_back(i);
+  chunk_start.push_back(n_imgs);
+  const uint32_t n_chunks = (uint32_t)chunk_start.size() - 1;
+  try {
   for (uint32_t k = 0; k < n_chunks; k++) {
-    const int slot = (int)(k % heic_b200_ctx::kPipe);
-    const uint32_t i0 = k * chunk, cnt = std::min(chunk, n_imgs - i0);
+    const int slot = (int)(ctx->pipe_next++ % (uint32_t)ctx->pipe_slots);
+    const uint32_t i0 = chunk_start[k], cnt = chunk_start[k + 1] - i0;
     if (!ctx->pipe_stream[slot]) CU(cudaStreamCreateWithFlags(&ctx->pipe_stream[slot], cudaStreamNonBlocking));
     if (!ctx->pipe_batch[slot]) {
       ctx->pipe_batch[slot] = std::make_unique<heic_b200_batch>();
       ctx->pipe_batch[slot]->ctx = ctx;
       ctx->pipe_batch[slot]->stream = ctx->pipe_stream[slot];
     }
-    harvest(slot);  // the slot's previous chunk (kernels, copies, status) is complete before its buffers are reused
+    harvest_slot(ctx, slot);  // the slot's previous chunk (kernels, copies, status) is complete before its buffers are reused
     heic_b200_batch* b = ctx->pipe_batch[slot].get();
     cudaStream_t st = b->stream;
     b->apply_transforms = apply_transforms != 0;
@@ -737,19 +767,42 @@ static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs
       }
     }
     CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, b->tiles.size() * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
-    pending[slot].busy = true;
-    pending[slot].tile0 = first_tile[i0];
-    pending[slot].n_tiles = b->tiles.size();
+    ctx->pipe_pending[slot].job = job.get();
+    ctx->pipe_pending[slot].tile0 = first_tile[i0];
+    ctx->pipe_pending[slot].n_tiles = b->tiles.size();
   }
-  for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++) harvest(slot);
+  } catch (...) {
+    // a chunk could not be queued: retire the chunks of this job that are already in flight, then report
+    for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++)
+      if (ctx->pipe_pending[slot].job == job.get()) {
+        cudaStreamSynchronize(ctx->pipe_stream[slot]);
+        ctx->pipe_pending[slot].job = nullptr;
+      }
+    throw;
+  }
+  return job.release();
+}
+
+static int64_t job_wait(heic_b200_job* job) {
+  std::unique_ptr<heic_b200_job> owner(job);
+  heic_b200_ctx* ctx = job->ctx;
+  CU(cudaSetDevice(ctx->device));
+  for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++)
+    if (ctx->pipe_pending[slot].job == job) harvest_slot(ctx, slot);
   size_t bad = 0;
-  for (size_t i = 0; i < first_tile[n_imgs]; i++)
-    if (s_out[i].code != 0) bad++;
+  for (size_t i = 0; i < job->n_tiles; i++)
+    if (job->status[i].code != 0) bad++;
   if (bad) {
     set_last_error(std::to_string(bad) + " tile(s) failed to decode (malformed slice data); see the per-tile status");
     return HEIC_E_BITSTREAM;
   }
   return 0;
+}
+
+static int64_t decode_grids_impl(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
+                                 size_t pitch, size_t image_stride, int32_t apply_transforms, uint8_t* y_out,
+                                 uint8_t* cb_out, uint8_t* cr_out, heic_tile_status* status) {
+  return job_wait(submit_grids(ctx, imgs, n_imgs, rgb_out, pitch, image_stride, apply_transforms, y_out, cb_out, cr_out, status));
 }
 
 int32_t heic_b200_decode_grids(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
@@ -758,6 +811,23 @@ int32_t heic_b200_decode_grids(heic_b200_ctx* ctx, const heic_image_desc* imgs, 
     if (!rgb_out) bail(HEIC_E_INVALID_ARG, "null output buffer");
     return decode_grids_impl(ctx, imgs, n_imgs, rgb_out, pitch, image_stride, apply_transforms, nullptr, nullptr, nullptr,
                              status);
+  }));
+}
+
+int32_t heic_b200_decode_grids_submit(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, uint8_t* rgb_out,
+                                      size_t pitch, size_t image_stride, int32_t apply_transforms, heic_tile_status* status,
+                                      heic_b200_job** out_job) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!rgb_out || !out_job) bail(HEIC_E_INVALID_ARG, "null argument");
+    *out_job = submit_grids(ctx, imgs, n_imgs, rgb_out, pitch, image_stride, apply_transforms, nullptr, nullptr, nullptr, status);
+    return 0;
+  }));
+}
+
+int32_t heic_b200_job_wait(heic_b200_job* job) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!job) bail(HEIC_E_INVALID_ARG, "null job");
+    return job_wait(job);
   }));
 }
 

@@ -253,6 +253,17 @@ int32_t heic_b200_decode_grids(heic_b200_ctx* ctx, const heic_image_desc* imgs, 
                                uint8_t* rgb_out, size_t pitch, size_t image_stride,
                                int32_t apply_transforms, heic_tile_status* status);
 
+/* Asynchronous form of the same call, for double-buffered serving loops: submit queues the host->device copies, the
+ * kernels and the device->host copies of all chunks and returns; heic_b200_job_wait blocks until the RGB and the status
+ * of that call are complete, returns its result (0 / HEIC_E_BITSTREAM) and frees the job.  Descriptors and bitstreams are
+ * consumed before submit returns; rgb_out and status must stay valid until the wait.  Several jobs may be in flight on
+ * one context (same thread); a later job's host->device copy and kernels overlap an earlier job's device->host copy. */
+typedef struct heic_b200_job heic_b200_job;
+int32_t heic_b200_decode_grids_submit(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs,
+                                      uint8_t* rgb_out, size_t pitch, size_t image_stride,
+                                      int32_t apply_transforms, heic_tile_status* status, heic_b200_job** out_job);
+int32_t heic_b200_job_wait(heic_b200_job* job);
+
 /* Same, planar YCbCr out (tile mosaic cropped to the output canvas, no colour conversion): Y plane
  * output_width x output_height, then Cb, Cr at half resolution (rounded up), per image.  */
 int32_t heic_b200_decode_grids_yuv(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs,

@@ -176,3 +176,26 @@ def test_launch_accounting(decoder, heic_file):
     n0 = decoder.launch_count()
     decoder.decode_grids([heic_file.primary])
     assert decoder.launch_count() - n0 >= 12  # cabac + 7 transform + intra + deblock + sao + colour
+
+
+def test_async_submit_wait_two_jobs_in_flight(decoder, heic_file, oracle_rgb):
+    """heic_b200_decode_grids_submit / _job_wait: two jobs in flight on one context, results independent and exact."""
+    base = heic_file.primary
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(48)
+    img2, keep = permuted_image(base, perm)
+    out_a = np.zeros((3, 3024, 4032, 3), np.uint8)
+    out_b = np.zeros((2, 3024, 4032, 3), np.uint8)
+    ja = decoder.submit_grids([base, base, base], out_a)
+    jb = decoder.submit_grids([img2, base], out_b)
+    decoder.wait_job(ja)
+    decoder.wait_job(jb)
+    for i in range(3):
+        assert np.array_equal(out_a[i], oracle_rgb)
+    assert np.array_equal(out_b[1], oracle_rgb)
+    for d, s in enumerate(perm):
+        r, c = divmod(d, 8)
+        rs, cs = divmod(int(s), 8)
+        hh = min(512, 3024 - r * 512, 3024 - rs * 512)
+        ww = min(512, 4032 - c * 512, 4032 - cs * 512)
+        assert np.array_equal(out_b[0, r * 512:r * 512 + hh, c * 512:c * 512 + ww], oracle_rgb[rs * 512:rs * 512 + hh, cs * 512:cs * 512 + ww])
