@@ -201,12 +201,20 @@ __device__ __forceinline__ void predict_block(const Ctu& c, int cidx, uint8_t* b
 #ifndef HEIC_INTRA_MIN_CTAS
 #define HEIC_INTRA_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, int warp_bytes, int log2_ctb_alloc) {
+__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, int warp_bytes, int log2_ctb_alloc, int clear_coeff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t tile = order[blockIdx.x];
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
-  if (A.status[tile].code != 0) return;
+  if (A.status[tile].code != 0) {
+    // a tile that failed to parse is not reconstructed, but its coefficient slots still go back to all-zero (below)
+    if (clear_coeff) {
+      uint4* z = reinterpret_cast<uint4*>(A.coeff + tp->coeff_off[0]);
+      const size_t n16 = (size_t)pp->n_tu * 24 * 2 / 16;
+      for (size_t i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
   const int wctb = pp->wctb, hctb = pp->hctb;
   volatile int* progress = reinterpret_cast<volatile int*>(smem_raw);
   const int progress_bytes = n_slots > 1 ? ((hctb * 4 + 15) & ~15) : 0;
@@ -310,6 +318,22 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
       if (lane < 8) c.dmask[lane] = 0;
       cp_async_wait_all();
       __syncwarp();
+      if (clear_coeff) {
+        // The residuals now live in shared memory: hand the CTU's coefficient slots back all-zero, which is what the
+        // next decode's CABAC stage needs (it only writes significant coefficients).  Coalesced fire-and-forget
+        // stores here replace a full-arena memset before every decode.
+        const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+        char* g0 = reinterpret_cast<char*>(A.coeff + tp->coeff_off[0] + (size_t)ctb_addr * n4sq * 16);
+        for (int i = lane * 16; i < n4sq * 32; i += 512) *reinterpret_cast<uint4*>(g0 + i) = zero;
+        if (n_planes == 3) {
+          char* g1 = reinterpret_cast<char*>(A.coeff + tp->coeff_off[1] + (size_t)ctb_addr * n4sq * 4);
+          char* g2 = reinterpret_cast<char*>(A.coeff + tp->coeff_off[2] + (size_t)ctb_addr * n4sq * 4);
+          for (int i = lane * 16; i < n4sq * 8; i += 512) {
+            *reinterpret_cast<uint4*>(g1 + i) = zero;
+            *reinterpret_cast<uint4*>(g2 + i) = zero;
+          }
+        }
+      }
       // ---- transform units of this CTB in z-order -----------------------------------------------------
       int idx = 0;
       while (idx < n4sq) {
@@ -379,7 +403,8 @@ int intra_warp_bytes(int log2_ctb) {
 
 }  // namespace
 
-cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, cudaStream_t stream) {
+cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, bool clear_coeff,
+                         cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
   const int wb = intra_warp_bytes(max_log2_ctb);
   const size_t smem = (n_slots > 1 ? (((size_t)max_hctb * 4 + 15) & ~(size_t)15) : 0) + (size_t)n_slots * wb;
@@ -389,7 +414,7 @@ cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ct
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, wb, max_log2_ctb);
+  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, wb, max_log2_ctb, clear_coeff ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -22,7 +22,9 @@ int transform_launches(int max_log2_tb);
 
 // Stage 3 — intra prediction + reconstruction (8.4.4.2), CTU wavefront per picture.
 // order: every tile index once, heaviest first (launch order of the one-CTA-per-picture grid)
-cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, cudaStream_t stream);
+// clear_coeff: zero every coefficient slot after consuming it (leaves the arena ready for the next decode's CABAC stage)
+cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, bool clear_coeff,
+                         cudaStream_t stream);
 
 // Stage 4 — deblocking (8.7.2), in place on the reconstruction arena.
 cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cudaStream_t stream);

@@ -145,6 +145,7 @@ struct heic_b200_batch {
   uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
   int max_log2_ctb = 4, max_log2_tb = 2, intra_slots = 1, max_hctb = 1;
   uint32_t stages_run = 0;
+  bool coeff_clean = false;   // the coefficient arena is all-zero (fresh memset, or the last intra stage cleared it)
   PinnedBuf h_bitstream, h_status, h_params;
   size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
   DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
@@ -375,6 +376,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   d_bitstream.ensure(bs_bytes + 16);
   d_params.ensure(params_bytes);
   d_tu.ensure(tu_words * 4);
+  if (coeff_elems * 2 > d_coeff.cap) coeff_clean = false;  // a fresh allocation is not zero
   d_coeff.ensure(coeff_elems * 2);
   d_recon.ensure(plane_bytes);
   d_final.ensure(plane_bytes);
@@ -398,7 +400,8 @@ void heic_b200_batch::run(uint32_t mask) {
   if (mask & HEIC_STAGE_CABAC) {
     // tu_map must be zero outside transform-unit origins, levels zero outside significant coefficients
     CU(cudaMemsetAsync(d_tu.p, 0, tu_words * 4, st));
-    CU(cudaMemsetAsync(d_coeff.p, 0, coeff_elems * 2, st));
+    if (!coeff_clean) CU(cudaMemsetAsync(d_coeff.p, 0, coeff_elems * 2, st));
+    coeff_clean = false;
     CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
     CU(cudaMemsetAsync(d_sao.p, 0, sao_words * 4, st));  // slices without SAO parse no parameters
     for (const CabacClass& c : classes) {
@@ -415,7 +418,8 @@ void heic_b200_batch::run(uint32_t mask) {
     // enough pictures to fill the GPU with one warp each: drop the intra-picture wavefront (no waiting at all)
     int slots = tiles.size() >= (size_t)ctx->intra_single_warp_tiles ? 1 : intra_slots;
     if (ctx->intra_slots > 0) slots = std::min(ctx->intra_slots, std::max(1, max_hctb));
-    CU(launch_intra(A, (const uint32_t*)((const uint8_t*)d_params.p + off_heavy), max_log2_ctb, max_hctb, slots, st));
+    CU(launch_intra(A, (const uint32_t*)((const uint8_t*)d_params.p + off_heavy), max_log2_ctb, max_hctb, slots, true, st));
+    coeff_clean = true;
     ctx->launches++;
   }
   if (mask & HEIC_STAGE_DEBLOCK) {

@@ -300,7 +300,8 @@ int32_t heic_b200_batch_status(heic_b200_batch* b, heic_tile_status* status /* n
 uint32_t heic_b200_batch_tile_count(const heic_b200_batch* b);
 
 /* Intermediate buffers of one tile, copied to host, for per-stage parity tests.  Layouts are
- * documented in DESIGN.md ("Data layout in HBM").  Any pointer may be NULL. */
+ * documented in DESIGN.md ("Data layout in HBM").  Any pointer may be NULL.  The coefficient buffers hold levels
+ * after the CABAC stage, residuals after the transform stage, and zeros once the intra stage has consumed them. */
 typedef struct heic_tile_dump {
   uint32_t* tu_map;      uint32_t tu_map_len;     /* one word per 4x4 luma block, CTB-major z-order  */
   int16_t*  coeff[3];    uint32_t coeff_len[3];   /* levels (after CABAC) or residual (after TRANSFORM) */
