@@ -32,41 +32,9 @@ __device__ __forceinline__ Window row_window(const uint8_t* row, int x, int pw) 
   return w;
 }
 
-// grid: flat over (tile, block of 8-sample groups of the tile); the groups of the three planes are numbered consecutively, row
-// by row, so CTAs stay full whatever the picture width is
-__global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_tile) {
-  const uint32_t tile = blockIdx.x / blocks_per_tile;
-  const TileParams* tp = A.tiles + tile;
-  const PicParams* pp = A.pics + tp->pic;
-  if (A.status[tile].code != 0) return;
-  uint32_t g = (blockIdx.x % blocks_per_tile) * blockDim.x + threadIdx.x;
-  const uint32_t gy = (uint32_t)(pp->w + 7) >> 3, gc = (uint32_t)((pp->w >> 1) + 7) >> 3;  // groups per row
-  const uint32_t n_y = gy * (uint32_t)pp->h, n_c = pp->chroma ? gc * (uint32_t)(pp->h >> 1) : 0u;
-  int cidx = 0;
-  if (g >= n_y) {
-    g -= n_y;
-    cidx = 1;
-    if (g >= n_c) {
-      g -= n_c;
-      cidx = 2;
-      if (g >= n_c) return;
-    }
-  }
-  const uint32_t gpr = cidx ? gc : gy;
-  const int y = (int)(g / gpr);
-  const int sub = cidx ? 1 : 0;
-  const int pw = pp->w >> sub, ph = pp->h >> sub, pitch = cidx ? pp->pitch_c : pp->pitch_y;
-  const int x = (int)(g % gpr) * 8;
-  if (x >= pw) return;  // plane widths are multiples of 4; pitches of 64, so the 8-byte access below stays inside the row
-  const uint8_t* src = A.recon + tp->plane_off[cidx];
-  uint8_t* dst = A.final_ + tp->plane_off[cidx];
-  const uint8_t* row = src + (size_t)y * pitch;
-  const int log2_cs = pp->log2_ctb - sub;
-  const uint32_t word = A.sao[tp->sao_off + (size_t)((y >> log2_cs) * pp->wctb + (x >> log2_cs)) * 4 + cidx];
-  const bool enabled = cidx == 0 ? tp->sao_luma : tp->sao_chroma;
-  const int type = enabled ? (int)(word & 3u) : 0;
-  const uint2 center = *reinterpret_cast<const uint2*>(row + x);
-  uint32_t out[2] = {center.x, center.y};
+// SAO of eight samples at (x, y) of one plane; `out` holds the deblocked samples on entry.
+__device__ __forceinline__ void sao8(uint32_t (&out)[2], const uint8_t* row, int x, int y, int pw, int ph, int pitch, uint32_t word,
+                                     int type) {
   if (type) {
     // the four offsets as one word of signed nibbles; entry 0 of the edge table (edgeIdx 2 -> 0) is zero
     const uint32_t offs = (word >> 8) & 0xffffu;
@@ -113,10 +81,58 @@ __global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_
       }
     }
   }
-  if (x + 8 <= pw) {
-    *reinterpret_cast<uint2*>(dst + (size_t)y * pitch + x) = make_uint2(out[0], out[1]);
-  } else {
-    *reinterpret_cast<uint32_t*>(dst + (size_t)y * pitch + x) = out[0];
+}
+
+// grid: flat over (tile, block of 16-sample groups of the tile); the groups of the three planes are numbered consecutively,
+// row by row, so CTAs stay full whatever the picture width is.  A thread moves 16 bytes; with SAO off for the CTB (the
+// common case in real streams) that is a plain 16-byte copy.
+__global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_tile) {
+  const uint32_t tile = blockIdx.x / blocks_per_tile;
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+  if (A.status[tile].code != 0) return;
+  uint32_t g = (blockIdx.x % blocks_per_tile) * blockDim.x + threadIdx.x;
+  const uint32_t gy = (uint32_t)(pp->w + 15) >> 4, gc = (uint32_t)((pp->w >> 1) + 15) >> 4;  // groups per row
+  const uint32_t n_y = gy * (uint32_t)pp->h, n_c = pp->chroma ? gc * (uint32_t)(pp->h >> 1) : 0u;
+  int cidx = 0;
+  if (g >= n_y) {
+    g -= n_y;
+    cidx = 1;
+    if (g >= n_c) {
+      g -= n_c;
+      cidx = 2;
+      if (g >= n_c) return;
+    }
+  }
+  const uint32_t gpr = cidx ? gc : gy;
+  const int y = (int)(g / gpr);
+  const int sub = cidx ? 1 : 0;
+  const int pw = pp->w >> sub, ph = pp->h >> sub, pitch = cidx ? pp->pitch_c : pp->pitch_y;
+  const int x = (int)(g % gpr) * 16;  // plane widths are multiples of 4, pitches of 64: the 16-byte access stays inside the row
+  const uint8_t* src = A.recon + tp->plane_off[cidx];
+  uint8_t* dst = A.final_ + tp->plane_off[cidx];
+  const uint8_t* row = src + (size_t)y * pitch;
+  const int log2_cs = pp->log2_ctb - sub;
+  const bool enabled = cidx == 0 ? tp->sao_luma : tp->sao_chroma;
+  const uint32_t* sao_row = A.sao + tp->sao_off + (size_t)((y >> log2_cs) * pp->wctb) * 4 + cidx;
+  const uint4 center = *reinterpret_cast<const uint4*>(row + x);
+  uint32_t lo[2] = {center.x, center.y}, hi[2] = {center.z, center.w};
+  if (enabled) {
+    const uint32_t w0 = sao_row[(size_t)(x >> log2_cs) * 4];
+    if (w0 & 3u) sao8(lo, row, x, y, pw, ph, pitch, w0, (int)(w0 & 3u));
+    if (x + 8 < pw) {
+      const uint32_t w1 = sao_row[(size_t)((x + 8) >> log2_cs) * 4];
+      if (w1 & 3u) sao8(hi, row, x + 8, y, pw, ph, pitch, w1, (int)(w1 & 3u));
+    }
+  }
+  uint8_t* o = dst + (size_t)y * pitch + x;
+  if (x + 16 <= pw) {
+    *reinterpret_cast<uint4*>(o) = make_uint4(lo[0], lo[1], hi[0], hi[1]);
+  } else {  // ragged right edge: 4, 8 or 12 valid samples
+    const int n = pw - x;
+    *reinterpret_cast<uint32_t*>(o) = lo[0];
+    if (n > 4) *reinterpret_cast<uint32_t*>(o + 4) = lo[1];
+    if (n > 8) *reinterpret_cast<uint32_t*>(o + 8) = hi[0];
   }
 }
 
@@ -124,7 +140,7 @@ __global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_
 
 cudaError_t launch_sao(const Arenas& A, uint32_t max_pitch, uint32_t max_h, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const uint32_t groups = ((max_pitch + 7) / 8) * max_h * 2;  // upper bound on the 8-sample groups of a tile
+  const uint32_t groups = ((max_pitch + 15) / 16) * max_h * 2;  // upper bound on the 16-sample groups of a tile
   const uint32_t bpt = (groups + 255) / 256;
   sao_kernel<<<A.n_tiles * bpt, 256, 0, stream>>>(A, bpt);
   return cudaGetLastError();
