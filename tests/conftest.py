@@ -55,10 +55,21 @@ def oracle_tiles(heic_file):
     return get
 
 
-@pytest.fixture(scope="session")
-def decoder(built):
+@pytest.fixture(scope="session", params=["auto", "thread_per_substream"])
+def decoder(built, request):
+    """Both CABAC mappings: 'auto' picks warp-per-substream for the small loads the tests use; the second context forces
+    the 32-tiles-per-CTA thread-per-substream kernel that large batches (bench.py) run."""
     import heif_b200
 
-    dec = heif_b200.HeicDecoder(device=0)
+    old = os.environ.get("HEIC_B200_LOW_LATENCY_TILES")
+    if request.param == "thread_per_substream":
+        os.environ["HEIC_B200_LOW_LATENCY_TILES"] = "0"
+    try:
+        dec = heif_b200.HeicDecoder(device=0)
+    finally:
+        if old is None:
+            os.environ.pop("HEIC_B200_LOW_LATENCY_TILES", None)
+        else:
+            os.environ["HEIC_B200_LOW_LATENCY_TILES"] = old
     yield dec
     dec.close()
