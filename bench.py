@@ -311,7 +311,7 @@ def main():
     cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
-    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, 128), args.batch)  # pinned host RGB: 36.6 MB per image per rank
+    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, 64), args.batch)  # pinned host RGB: 2 x 36.6 MB per image per rank
     out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)

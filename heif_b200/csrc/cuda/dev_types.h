@@ -105,6 +105,13 @@ struct TileParams {
   uint64_t wpp_off;             // bytes: WPP context snapshots, NUM_CTX_PAD per CTB row
 };
 
+// Transform classes: one list (and one launch) per transform size; 4x4 luma (DST) and chroma (DCT) apart.
+enum { LIST_32 = 0, LIST_16 = 1, LIST_8 = 2, LIST_4Y = 3, LIST_4C = 4, LIST_CLASSES = 5 };
+enum { LIST_COUNT_STRIDE = 32 };  // words between the per-class counters: one cache line each, so their atomics do not serialise
+struct uint2_t {
+  uint32_t x, y;
+};
+
 struct TileStatusDev {
   int32_t code;
   uint32_t bins, ctus, reserved;
@@ -128,6 +135,10 @@ struct Arenas {
   uint8_t* wpp_save;
   TileStatusDev* status;
   uint32_t n_tiles;
+  // coded transform blocks, one dense list per transform class (built by the transform stage from tu_map)
+  uint2_t* tu_list;              // {tile, tu_map entry | colour component << 30}
+  uint32_t* list_count;          // LIST_CLASSES counters, LIST_COUNT_STRIDE words apart
+  uint32_t list_off[5];          // first element of each class in tu_list
 };
 
 }  // namespace dev

@@ -96,6 +96,7 @@ struct PipePending {
 
 struct heic_b200_ctx {
   int device = 0;
+  int n_sm = 148;
   cudaStream_t stream = nullptr;
   CabacTabs* d_tabs = nullptr;
   uint64_t launches = 0;
@@ -149,7 +150,8 @@ struct heic_b200_batch {
   PinnedBuf h_bitstream, h_status, h_params;
   size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
   DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
-      d_qp, d_sao, d_wpp, d_status, d_rgb;
+      d_qp, d_sao, d_wpp, d_status, d_rgb, d_list, d_list_count;
+  uint32_t list_off[LIST_CLASSES] = {};
   Arenas arenas() const {
     Arenas a;
     a.bitstream = (const uint8_t*)d_bitstream.p;
@@ -169,6 +171,9 @@ struct heic_b200_batch {
     a.wpp_save = (uint8_t*)d_wpp.p;
     a.status = (TileStatusDev*)d_status.p;
     a.n_tiles = (uint32_t)tiles.size();
+    a.tu_list = (uint2_t*)d_list.p;
+    a.list_count = (uint32_t*)d_list_count.p;
+    for (int k = 0; k < LIST_CLASSES; k++) a.list_off[k] = list_off[k];
     return a;
   }
   void load(const heic_image_desc* imgs, uint32_t n_imgs, bool with_rgb);
@@ -376,6 +381,9 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   d_bitstream.ensure(bs_bytes + 16);
   d_params.ensure(params_bytes);
   d_tu.ensure(tu_words * 4);
+  if (tu_words >= (1ull << 31)) bail(HEIC_E_UNSUPPORTED, "batch too large: more than 2^31 4x4 blocks in one load");
+  d_list.ensure(transform_list_layout(tu_words, list_off) * sizeof(uint2_t));
+  d_list_count.ensure(LIST_CLASSES * LIST_COUNT_STRIDE * sizeof(uint32_t));
   if (coeff_elems * 2 > d_coeff.cap) coeff_clean = false;  // a fresh allocation is not zero
   d_coeff.ensure(coeff_elems * 2);
   d_recon.ensure(plane_bytes);
@@ -411,7 +419,7 @@ void heic_b200_batch::run(uint32_t mask) {
     }
   }
   if (mask & HEIC_STAGE_TRANSFORM) {
-    CU(launch_transform(A, max_tu, max_log2_tb, st));
+    CU(launch_transform(A, max_tu, max_log2_tb, ctx->n_sm, st));
     ctx->launches += transform_launches(max_log2_tb);
   }
   if (mask & HEIC_STAGE_INTRA) {
@@ -512,6 +520,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     CU(cudaGetDeviceProperties(&prop, c->device));
     if (prop.major < 10)
       bail(HEIC_E_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 class; the kernels are built for sm_100a only");
+    CU(cudaDeviceGetAttribute(&c->n_sm, cudaDevAttrMultiProcessorCount, c->device));
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     static CabacTabs tabs;
     build_cabac_tabs(tabs);

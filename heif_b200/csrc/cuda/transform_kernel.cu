@@ -1,16 +1,18 @@
 // Stage 2: scaling (H.265 8.6.4.2 with the 7.4.5 scaling factors) + inverse DST-4 / DCT-4..32 (8.6.4.2),
 // in place on the coefficient arena.  The reference has none of this (slice.rs:253-255 is todo!()).
 //
-// Small integer butterflies, HBM-bound.  One launch per (component kind, transform size) so that every CTA of
-// a launch runs the same straight-line butterfly and the instruction cache holds it (a single kernel with all
-// sizes was instruction-fetch bound).  A warp owns 64 consecutive tu_map entries (a 32x32 luma area and its
-// two 16x16 chroma areas) and sweeps the aligned slots of the launch's size:
-//   n >= 8: 32/n transform blocks at a time; a lane runs one n-point 1-D transform per pass (columns, then
-//           rows) as an even/odd partial butterfly in registers; the passes are joined through a padded
-//           (conflict-free) shared-memory tile and the residual goes back to HBM in lane-contiguous words;
-//   n == 4: one lane per block, both passes in registers, 32 blocks per warp step, 32-byte loads/stores.
-// Only coded blocks (cbf = 1) are read or written, so DRAM traffic is 2 B in + 2 B out per coded sample.
+// Small integer butterflies.  A first pass over tu_map appends every coded block (cbf = 1) to the dense list of its
+// transform size; then one launch per size works through its list, so every warp step is full of coded blocks and every
+// CTA of a launch runs the same straight-line butterfly (a single kernel with all sizes was instruction-fetch bound, and
+// sweeping tu_map in place left most lanes of a step without a block):
+//   n >= 8: 32/n blocks per warp step; a lane runs one n-point 1-D transform per pass (columns, then rows) as an
+//           even/odd partial butterfly in registers; the passes are joined through a padded (conflict-free)
+//           shared-memory tile and the residual goes back to HBM in lane-contiguous words;
+//   n == 4: one lane per block, both passes in registers, 32-byte loads/stores.
+// Only coded blocks are read or written, so DRAM traffic is 2 B in + 2 B out per coded sample (+ 8 B per block of list).
 #include <cuda_runtime.h>
+
+#include <algorithm>
 
 #include "kernels.h"
 
@@ -88,46 +90,151 @@ __device__ __forceinline__ void transform_1d(const int (&x)[N], int (&y)[N], int
 __device__ const uint8_t kLevelScale[6] = {40, 45, 51, 57, 64, 72};
 __device__ const uint8_t kChromaQp[14] = {29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37};  // qPi 30..43
 
-struct WarpCtx {
+constexpr int kWarpsPerCta = 8;
+constexpr int kTmpPerWarp = 32 * 34;  // int16 elements: one 32x32 block with padded rows
+
+// ---- list construction ---------------------------------------------------------------------------------------
+// A CTA classifies kListPerCta consecutive tu_map entries of one tile, four per thread.  The per-class item counts are
+// packed in one 64-bit word (12 bits per class) so a single warp scan places every thread's items; a warp reserves its
+// space in the CTA with shared-memory atomics and the CTA reserves its space in every list with one global atomic per
+// class.  Item order within a list is not deterministic; the blocks are independent, so the results are.
+constexpr int kListThreads = 256;
+constexpr int kListPerCta = 4 * kListThreads;
+
+// classes of the (up to) three coded blocks of a tu_map word, 3 bits each (7: none)
+__device__ __forceinline__ uint32_t classify(uint32_t w, bool chroma) {
+  uint32_t cy = 7, cb = 7, cr = 7;
+  if (w & TU_ORIGIN) {
+    const int lg = (int)tu_log2(w);
+    if (w & TU_CBF_Y) cy = 5 - lg;  // LIST_32 .. LIST_4Y
+    // chroma rides on the luma TU of twice its size, or on blkIdx 3 of a split 8x8
+    if (chroma && (lg > 2 || (w & TU_HAS_CHROMA))) {
+      const uint32_t cc = lg == 5 ? LIST_16 : lg == 4 ? LIST_8 : LIST_4C;
+      if (w & TU_CBF_CB) cb = cc;
+      if (w & TU_CBF_CR) cr = cc;
+    }
+  }
+  return cy | (cb << 3) | (cr << 6);
+}
+
+__global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_t blocks_per_tile) {
+  __shared__ uint32_t cta_cnt[LIST_CLASSES], cta_base[LIST_CLASSES], warp_base[kListThreads / 32][LIST_CLASSES];
+  const uint32_t tile = blockIdx.x / blocks_per_tile;
+  const uint32_t first = (blockIdx.x % blocks_per_tile) * kListPerCta;
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (A.status[tile].code != 0 || first >= (uint32_t)pp->n_tu) return;  // uniform over the CTA
+  if (threadIdx.x < LIST_CLASSES) cta_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const bool chroma = pp->chroma != 0;
+  const uint32_t i0 = first + threadIdx.x * 4;  // n_tu and tu_off are multiples of 16
+  uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+  if (i0 < (uint32_t)pp->n_tu) wv = *reinterpret_cast<const uint4*>(A.tu_map + tp->tu_off + i0);
+  const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+  uint32_t cls[4];
+  unsigned long long mine = 0;  // items of this thread per class, 12 bits each
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    cls[e] = 0x1ffu;
+    if (w[e]) {
+      cls[e] = classify(w[e], chroma);
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const uint32_t k = (cls[e] >> (3 * c)) & 7u;
+        if (k < LIST_CLASSES) mine += 1ull << (12 * k);
+      }
+    }
+  }
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned long long total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane < LIST_CLASSES) {
+    const uint32_t n = (uint32_t)(total >> (12 * lane)) & 0xfffu;
+    warp_base[warp][lane] = n ? atomicAdd(cta_cnt + lane, n) : 0u;
+  }
+  __syncthreads();
+  if (threadIdx.x < LIST_CLASSES)
+    cta_base[threadIdx.x] = A.list_off[threadIdx.x] +
+                            (cta_cnt[threadIdx.x] ? atomicAdd(A.list_count + threadIdx.x * LIST_COUNT_STRIDE, cta_cnt[threadIdx.x]) : 0u);
+  __syncthreads();
+  if (!mine) return;
+  unsigned long long run = incl - mine;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (cls[e] == 0x1ffu) continue;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint32_t k = (cls[e] >> (3 * c)) & 7u;
+      if (k < LIST_CLASSES) {
+        uint2_t v;
+        v.x = tile;
+        v.y = (i0 + e) | ((uint32_t)c << 30);
+        A.tu_list[(size_t)cta_base[k] + warp_base[warp][k] + ((uint32_t)(run >> (12 * k)) & 0xfffu)] = v;
+        run += 1ull << (12 * k);
+      }
+    }
+  }
+}
+
+// A coded block named by a list item.
+struct Item {
   const PicParams* pp;
   const TileParams* tp;
-  const ScalingSet* sc;
-  int16_t* tmp;   // this warp's padded transpose tile
-  const uint32_t* tu;  // the region's 64 tu_map words
-  int n_entries;       // valid entries of the region (< 64 only at the end of a CTB-16 picture)
-  int lane;
+  int16_t* blk;
+  uint32_t w;
+  int cidx;
 };
+__device__ __forceinline__ Item fetch_item(const Arenas& A, uint2_t it) {
+  Item r;
+  r.tp = A.tiles + it.x;
+  r.pp = A.pics + r.tp->pic;
+  const uint32_t entry = it.y & 0x3fffffffu;
+  r.cidx = (int)(it.y >> 30);
+  r.w = A.tu_map[r.tp->tu_off + entry];
+  // luma: 16 coefficients per tu_map entry; chroma: 4, at the entry of the 8x8 luma area the block belongs to
+  r.blk = A.coeff + r.tp->coeff_off[r.cidx] + (r.cidx ? (size_t)(entry & ~3u) * 4 : (size_t)entry * 16);
+  return r;
+}
+__device__ __forceinline__ int item_scale(const Item& t) {  // levelScale[qP % 6] << (qP / 6), 8.6.2 / 8.6.4.2
+  int qp = (int)tu_qp(t.w);
+  if (t.cidx) {
+    int qpi = qp + (t.cidx == 1 ? t.pp->pps_cb_qp_offset + t.tp->slice_cb_qp_offset : t.pp->pps_cr_qp_offset + t.tp->slice_cr_qp_offset);
+    qpi = min(57, max(0, qpi));
+    qp = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
+  }
+  return (int)kLevelScale[qp % 6] << (qp / 6);
+}
 
-// One transform size of one colour component over the warp's region.
-//   luma   (CIDX 0): slots of (N/4)^2 tu_map entries; block at coeff + slot * N*N
-//   chroma (CIDX>0): chroma NxN belongs to the luma TU of size 2N (or to blkIdx 3 of a split 8x8 when N = 4)
-template <int N, int CIDX>
-__device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* region base of this component */) {
-  constexpr int K = 32 / N;                      // blocks per batch
-  constexpr int LOG2 = N == 4 ? 2 : N == 8 ? 3 : N == 16 ? 4 : 5;
-  constexpr int EPB = CIDX == 0 ? (N / 4) * (N / 4) : (N / 2) * (N / 2);  // tu_map entries per block slot
-  constexpr int SLOTS = 64 / EPB;
-  constexpr int S = N + 2;                       // padded row stride (int16) of the transpose tile
-  constexpr bool DST = (CIDX == 0 && N == 4);
-  const int k = c.lane / N, col = c.lane % N;
-  for (int batch = 0; batch < (SLOTS + K - 1) / K; batch++) {
-    const int slot = batch * K + k;
-    bool active = false;
-    uint32_t w;
-    {
-      const bool has_slot = slot < SLOTS && slot * EPB < c.n_entries;
-      const int entry = has_slot ? slot * EPB : 0;
-      w = c.tu[entry];  // lanes of one block read the same word (broadcast)
-      const uint32_t cbf_bit = CIDX == 0 ? TU_CBF_Y : (CIDX == 1 ? TU_CBF_CB : TU_CBF_CR);
-      if (CIDX == 0) active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 && (w & cbf_bit);
-      else active = (w & TU_ORIGIN) && tu_log2(w) == LOG2 + 1 && (w & cbf_bit);
-      active = active && has_slot;
-    }
-    if (!__any_sync(0xffffffffu, active)) continue;
-
-    int16_t* blk = coeff + (size_t)slot * (N * N);
-    int16_t* t = c.tmp + k * (N * S);
-    const bool tskip = active && tu_tskip(w, CIDX);
+// ---- n >= 8: one launch per size over its list ------------------------------------------------------------------
+template <int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, int cls) {
+  constexpr int K = 32 / N;  // blocks per warp step
+  constexpr int LOG2 = N == 8 ? 3 : N == 16 ? 4 : 5;
+  constexpr int S = N + 2;   // padded row stride (int16) of the transpose tile
+  __shared__ __align__(16) int16_t tmp_all[kWarpsPerCta][kTmpPerWarp];
+  __shared__ int16_t* blk_of[kWarpsPerCta][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = lane / N, col = lane % N;
+  const uint32_t count = A.list_count[cls * LIST_COUNT_STRIDE];
+  const uint2_t* list = A.tu_list + A.list_off[cls];
+  int16_t* tmp = tmp_all[warp];
+  int16_t* t = tmp + k * (N * S);
+  const uint32_t steps = (count + K - 1) / K;
+  for (uint32_t step = blockIdx.x * kWarpsPerCta + warp; step < steps; step += gridDim.x * kWarpsPerCta) {
+    const uint32_t idx = step * K + k;
+    const bool active = idx < count;
+    uint2_t it;
+    it.x = it.y = 0;
+    if (active) it = list[idx];
+    const Item item = fetch_item(A, it);  // item 0 of tile 0 for the idle lanes of the last step: read, never written
+    int16_t* blk = item.blk;
+    if (col == 0) blk_of[warp][k] = blk;
+    const bool tskip = active && tu_tskip(item.w, item.cidx);
     // ---- scaling + first (column) pass -------------------------------------------------------
     int x[N], y[N];
     int nz_rows = 0;
@@ -142,7 +249,7 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
 #pragma unroll
     for (int o = 16; o; o >>= 1) nz1 = max(nz1, __shfl_xor_sync(0xffffffffu, nz1, o));
     const uint32_t col_mask = __ballot_sync(0xffffffffu, nz_rows > 0);
-    // highest non-zero column index + 1 within any block of the batch
+    // highest non-zero column index + 1 within any block of the step
     int nz2 = 0;
 #pragma unroll
     for (int g = 0; g < K; g++) {
@@ -150,17 +257,12 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
       nz2 = max(nz2, 32 - __clz(mg));
     }
     if (active) {
-      int qp = (int)tu_qp(w);
-      if (CIDX) {
-        int qpi = qp + (CIDX == 1 ? c.pp->pps_cb_qp_offset + c.tp->slice_cb_qp_offset
-                                  : c.pp->pps_cr_qp_offset + c.tp->slice_cr_qp_offset);
-        qpi = min(57, max(0, qpi));
-        qp = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
-      }
-      const int scale = (int)kLevelScale[qp % 6] << (qp / 6);
+      const int scale = item_scale(item);
       const uint8_t* m = nullptr;
-      if (c.pp->scaling_enabled && !(tskip && N > 4))
-        m = N == 4 ? c.sc->f4[CIDX] : N == 8 ? c.sc->f8[CIDX] : N == 16 ? c.sc->f16[CIDX] : c.sc->f32[CIDX];
+      if (item.pp->scaling_enabled && !tskip) {
+        const ScalingSet* sc = A.scaling + item.pp->scaling_set;
+        m = N == 8 ? sc->f8[item.cidx] : N == 16 ? sc->f16[item.cidx] : sc->f32[item.cidx];
+      }
       constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
 #pragma unroll
       for (int j = 0; j < N; j++) {
@@ -183,7 +285,7 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
 #pragma unroll
       for (int i = 0; i < N; i++) y[i] = x[i];  // passed through; the rotation happens in the second pass
     } else {
-      transform_1d<N, DST>(x, y, nz1);
+      transform_1d<N, false>(x, y, nz1);
 #pragma unroll
       for (int i = 0; i < N; i++) y[i] = clip16((y[i] + 64) >> 7);
     }
@@ -205,7 +307,7 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
 #pragma unroll
       for (int i = 0; i < N; i++) y[i] = ((x[i] << 7) + 2048) >> 12;
     } else {
-      transform_1d<N, DST>(x, y, nz2);
+      transform_1d<N, false>(x, y, nz2);
 #pragma unroll
       for (int i = 0; i < N; i++) y[i] = clip16((y[i] + 2048) >> 12);
     }
@@ -219,56 +321,21 @@ __device__ __forceinline__ void run_size(const WarpCtx& c, int16_t* coeff /* reg
     __syncwarp();
     // ---- coalesced store of the residual blocks (pairs of int16) ----------------------------------
     {
-      constexpr int PAIRS = N * N / 2;            // per block
-      constexpr int TOTAL = K * PAIRS;            // per batch, lane-consecutive
+      constexpr int PAIRS = N * N / 2;  // per block
+      const uint32_t n_active = min((uint32_t)K, count - step * K);
+#pragma unroll
+      for (int g = 0; g < K; g++) {
+        if ((uint32_t)g >= n_active) break;  // warp-uniform
+        uint32_t* dst = reinterpret_cast<uint32_t*>(blk_of[warp][g]);
+        const int16_t* src = tmp + g * (N * S);
 #pragma unroll 4
-      for (int p = c.lane; p < TOTAL; p += 32) {
-        const int g = p / PAIRS, q = p % PAIRS;
-        const int r = q / (N / 2), cp = q % (N / 2);
-        const bool g_active = __shfl_sync(0xffffffffu, active ? 1 : 0, g * N) != 0;
-        const int g_slot = batch * K + g;
-        if (g_active) {
-          uint32_t v = *reinterpret_cast<const uint32_t*>(c.tmp + g * (N * S) + r * S + 2 * cp);
-          *reinterpret_cast<uint32_t*>(coeff + (size_t)g_slot * (N * N) + 2 * q) = v;
+        for (int q = lane; q < PAIRS; q += 32) {
+          const int r = q / (N / 2), cp = q % (N / 2);
+          dst[q] = *reinterpret_cast<const uint32_t*>(src + r * S + 2 * cp);
         }
       }
     }
     __syncwarp();
-  }
-}
-
-constexpr int kWarpsPerCta = 8;
-constexpr uint32_t kRegionsPerCta = 64;
-constexpr int kTmpPerWarp = 32 * 34;  // int16 elements: one 32x32 block with padded rows
-
-// ---- n >= 8: one launch per (CIDX kind, N) ------------------------------------------------------------------
-// KIND 0: luma, KIND 1: chroma (Cb then Cr)
-template <int N, int KIND>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A) {
-  __shared__ __align__(16) int16_t tmp_all[kWarpsPerCta][kTmpPerWarp];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tile = blockIdx.x;
-  const TileParams* tp = A.tiles + tile;
-  const PicParams* pp = A.pics + tp->pic;
-  if (A.status[tile].code != 0) return;
-  if (KIND == 1 && !pp->chroma) return;
-  WarpCtx c;
-  c.pp = pp;
-  c.tp = tp;
-  c.sc = A.scaling + pp->scaling_set;
-  c.tmp = tmp_all[warp];
-  c.lane = lane;
-  // a CTA sweeps kRegionsPerCta consecutive regions, one per warp at a time (fewer, longer-lived CTAs)
-  const uint32_t r_end = min((blockIdx.y + 1) * kRegionsPerCta, ((uint32_t)pp->n_tu + 63u) / 64u);
-  for (uint32_t region = blockIdx.y * kRegionsPerCta + warp; region < r_end; region += kWarpsPerCta) {
-    c.tu = A.tu_map + tp->tu_off + (size_t)region * 64;
-    c.n_entries = min(64, pp->n_tu - (int)region * 64);
-    if (KIND == 0) {
-      run_size<N, 0>(c, A.coeff + tp->coeff_off[0] + (size_t)region * 1024);
-    } else {
-      run_size<N, 1>(c, A.coeff + tp->coeff_off[1] + (size_t)region * 256);
-      run_size<N, 2>(c, A.coeff + tp->coeff_off[2] + (size_t)region * 256);
-    }
   }
 }
 
@@ -282,122 +349,102 @@ __device__ __forceinline__ void idct4(const int (&x)[4], int (&y)[4]) {
   y[3] = e0 - o0;
 }
 
-template <int CIDX>
-__device__ __forceinline__ void block4(int16_t* blk, uint32_t w, const PicParams* pp, const TileParams* tp, const ScalingSet* sc) {
-  const uint4 in0 = reinterpret_cast<const uint4*>(blk)[0], in1 = reinterpret_cast<const uint4*>(blk)[1];
-  const uint32_t raw[8] = {in0.x, in0.y, in0.z, in0.w, in1.x, in1.y, in1.z, in1.w};
-  int qp = (int)tu_qp(w);
-  if (CIDX) {
-    int qpi = qp + (CIDX == 1 ? pp->pps_cb_qp_offset + tp->slice_cb_qp_offset : pp->pps_cr_qp_offset + tp->slice_cr_qp_offset);
-    qpi = min(57, max(0, qpi));
-    qp = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
-  }
-  const int scale = (int)kLevelScale[qp % 6] << (qp / 6);
-  uint32_t mraw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
-  if (pp->scaling_enabled) {
-    const uint4 mv = *reinterpret_cast<const uint4*>(sc->f4[CIDX]);
-    mraw[0] = mv.x, mraw[1] = mv.y, mraw[2] = mv.z, mraw[3] = mv.w;
-  }
-  int d[16];
+// DST: luma 4x4 (intra blocks use the DST-VII, 8.6.4.2); otherwise the 4-point DCT of the chroma blocks.
+template <bool DST>
+__global__ void __launch_bounds__(256) transform4_kernel(Arenas A, int cls) {
+  const uint32_t count = A.list_count[cls * LIST_COUNT_STRIDE];
+  const uint2_t* list = A.tu_list + A.list_off[cls];
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+    const Item item = fetch_item(A, list[idx]);
+    int16_t* blk = item.blk;
+    const uint4 in0 = reinterpret_cast<const uint4*>(blk)[0], in1 = reinterpret_cast<const uint4*>(blk)[1];
+    const uint32_t raw[8] = {in0.x, in0.y, in0.z, in0.w, in1.x, in1.y, in1.z, in1.w};
+    const int scale = item_scale(item);
+    uint32_t mraw[4] = {0x10101010u, 0x10101010u, 0x10101010u, 0x10101010u};
+    if (item.pp->scaling_enabled) {
+      const uint4 mv = *reinterpret_cast<const uint4*>((A.scaling + item.pp->scaling_set)->f4[item.cidx]);
+      mraw[0] = mv.x, mraw[1] = mv.y, mraw[2] = mv.z, mraw[3] = mv.w;
+    }
+    int d[16];
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    const int lvl = (int)(int16_t)((raw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-    const int ms = (int)((mraw[i >> 2] >> (8 * (i & 3))) & 0xffu) * scale;
-    int v;
-    if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: 32-bit product (bdShift = 5 for 4x4, 8-bit)
-      v = (lvl * ms + 16) >> 5;
+    for (int i = 0; i < 16; i++) {
+      const int lvl = (int)(int16_t)((raw[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+      const int ms = (int)((mraw[i >> 2] >> (8 * (i & 3))) & 0xffu) * scale;
+      int v;
+      if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: 32-bit product (bdShift = 5 for 4x4, 8-bit)
+        v = (lvl * ms + 16) >> 5;
+      } else {
+        long long p = ((long long)lvl * ms + 16) >> 5;
+        v = (int)min(32767ll, max(-32768ll, p));
+      }
+      d[i] = min(32767, max(-32768, v));
+    }
+    int out[16];
+    if (tu_tskip(item.w, item.cidx)) {
+#pragma unroll
+      for (int i = 0; i < 16; i++) out[i] = ((d[i] << 7) + 2048) >> 12;
     } else {
-      long long p = ((long long)lvl * ms + 16) >> 5;
-      v = (int)min(32767ll, max(-32768ll, p));
+      int t[16];
+#pragma unroll
+      for (int cc = 0; cc < 4; cc++) {  // columns
+        const int x[4] = {d[cc], d[4 + cc], d[8 + cc], d[12 + cc]};
+        int y[4];
+        if (DST) dst4(x, y);
+        else idct4(x, y);
+#pragma unroll
+        for (int i = 0; i < 4; i++) t[i * 4 + cc] = clip16((y[i] + 64) >> 7);
+      }
+#pragma unroll
+      for (int r = 0; r < 4; r++) {  // rows
+        const int x[4] = {t[r * 4], t[r * 4 + 1], t[r * 4 + 2], t[r * 4 + 3]};
+        int y[4];
+        if (DST) dst4(x, y);
+        else idct4(x, y);
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[r * 4 + i] = clip16((y[i] + 2048) >> 12);
+      }
     }
-    d[i] = min(32767, max(-32768, v));
-  }
-  int out[16];
-  if (tu_tskip(w, CIDX)) {
+    uint32_t pk[8];
 #pragma unroll
-    for (int i = 0; i < 16; i++) out[i] = ((d[i] << 7) + 2048) >> 12;
-  } else {
-    int t[16];
-#pragma unroll
-    for (int cc = 0; cc < 4; cc++) {  // columns
-      const int x[4] = {d[cc], d[4 + cc], d[8 + cc], d[12 + cc]};
-      int y[4];
-      if (CIDX == 0) dst4(x, y);
-      else idct4(x, y);
-#pragma unroll
-      for (int i = 0; i < 4; i++) t[i * 4 + cc] = clip16((y[i] + 64) >> 7);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) {  // rows
-      const int x[4] = {t[r * 4], t[r * 4 + 1], t[r * 4 + 2], t[r * 4 + 3]};
-      int y[4];
-      if (CIDX == 0) dst4(x, y);
-      else idct4(x, y);
-#pragma unroll
-      for (int i = 0; i < 4; i++) out[r * 4 + i] = clip16((y[i] + 2048) >> 12);
-    }
-  }
-  uint32_t pk[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) pk[i] = ((uint32_t)out[2 * i] & 0xffffu) | ((uint32_t)out[2 * i + 1] << 16);
-  reinterpret_cast<uint4*>(blk)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  reinterpret_cast<uint4*>(blk)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-}
-
-// KIND 0: luma 4x4 TUs (a thread per tu_map entry); KIND 1: chroma 4x4 (a thread per 8x8 luma area and component)
-template <int KIND>
-__global__ void __launch_bounds__(256) transform4_kernel(Arenas A) {
-  const uint32_t tile = blockIdx.x;
-  const TileParams* tp = A.tiles + tile;
-  const PicParams* pp = A.pics + tp->pic;
-  if (A.status[tile].code != 0) return;
-  const ScalingSet* sc = A.scaling + pp->scaling_set;
-  const uint32_t* tu = A.tu_map + tp->tu_off;
-  const uint32_t i = blockIdx.y * blockDim.x + threadIdx.x;
-  if (KIND == 0) {
-    if (i >= (uint32_t)pp->n_tu) return;
-    const uint32_t w = tu[i];
-    if ((w & TU_ORIGIN) && tu_log2(w) == 2 && (w & TU_CBF_Y)) block4<0>(A.coeff + tp->coeff_off[0] + (size_t)i * 16, w, pp, tp, sc);
-  } else {
-    if (!pp->chroma) return;
-    const uint32_t slot = i >> 1, comp = i & 1;  // Cb / Cr of one slot on adjacent lanes
-    if (slot * 4 >= (uint32_t)pp->n_tu) return;
-    uint32_t w = tu[slot * 4];
-    bool ok = false;
-    if ((w & TU_ORIGIN) && tu_log2(w) == 3) ok = true;             // 8x8 luma TU -> 4x4 chroma
-    else if ((w & TU_ORIGIN) && tu_log2(w) == 2) {                  // split 8x8: chroma rides on blkIdx 3
-      w = tu[slot * 4 + 3];
-      ok = (w & TU_ORIGIN) && (w & TU_HAS_CHROMA);
-    }
-    if (!ok) return;
-    if (comp == 0) {
-      if (w & TU_CBF_CB) block4<1>(A.coeff + tp->coeff_off[1] + (size_t)slot * 16, w, pp, tp, sc);
-    } else {
-      if (w & TU_CBF_CR) block4<2>(A.coeff + tp->coeff_off[2] + (size_t)slot * 16, w, pp, tp, sc);
-    }
+    for (int i = 0; i < 8; i++) pk[i] = ((uint32_t)out[2 * i] & 0xffffu) | ((uint32_t)out[2 * i + 1] << 16);
+    reinterpret_cast<uint4*>(blk)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    reinterpret_cast<uint4*>(blk)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
 }  // namespace
 
-cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, cudaStream_t stream) {
+// Worst-case list sizes for `total_tu` tu_map entries: class offsets (elements) and the total, for the batch's allocation.
+size_t transform_list_layout(size_t total_tu, uint32_t off[LIST_CLASSES]) {
+  const size_t cap[LIST_CLASSES] = {total_tu / 64 + 1, total_tu / 16 + total_tu / 32 + 1, total_tu / 4 + total_tu / 8 + 1,
+                                    total_tu + 1, total_tu / 2 + 1};
+  size_t o = 0;
+  for (int k = 0; k < LIST_CLASSES; k++) {
+    off[k] = (uint32_t)o;
+    o += cap[k];
+  }
+  return o;
+}
+
+cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, int n_sm, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const uint32_t regions = (max_tu_per_tile + 63u) / 64u;
-  const dim3 grid(A.n_tiles, (regions + kRegionsPerCta - 1) / kRegionsPerCta), block(kWarpsPerCta * 32);
-  if (max_log2_tb >= 5) {
-    transform_kernel<32, 0><<<grid, block, 0, stream>>>(A);
-    transform_kernel<16, 1><<<grid, block, 0, stream>>>(A);
-  }
-  if (max_log2_tb >= 4) {
-    transform_kernel<16, 0><<<grid, block, 0, stream>>>(A);
-    transform_kernel<8, 1><<<grid, block, 0, stream>>>(A);
-  }
-  transform_kernel<8, 0><<<grid, block, 0, stream>>>(A);
-  transform4_kernel<0><<<dim3(A.n_tiles, (max_tu_per_tile + 255) / 256), 256, 0, stream>>>(A);
-  transform4_kernel<1><<<dim3(A.n_tiles, (max_tu_per_tile / 2 + 255) / 256), 256, 0, stream>>>(A);
+  cudaError_t e = cudaMemsetAsync(A.list_count, 0, LIST_CLASSES * LIST_COUNT_STRIDE * sizeof(uint32_t), stream);
+  if (e != cudaSuccess) return e;
+  const uint32_t bpt = (max_tu_per_tile + kListPerCta - 1) / kListPerCta;
+  tu_list_kernel<<<A.n_tiles * bpt, kListThreads, 0, stream>>>(A, bpt);
+  // the list lengths stay on the device: fixed grids sized to the machine stride over them
+  const size_t total = (size_t)A.n_tiles * max_tu_per_tile;
+  auto grid = [&](size_t max_steps, int resident) {
+    return (unsigned)std::max<size_t>(1, std::min<size_t>((max_steps + kWarpsPerCta - 1) / kWarpsPerCta, (size_t)n_sm * resident));
+  };
+  if (max_log2_tb >= 5) transform_kernel<32><<<grid(total / 64 + 1, 3), kWarpsPerCta * 32, 0, stream>>>(A, LIST_32);
+  if (max_log2_tb >= 4) transform_kernel<16><<<grid(total / 32 + 1, 4), kWarpsPerCta * 32, 0, stream>>>(A, LIST_16);
+  transform_kernel<8><<<grid(total / 16 + 1, 6), kWarpsPerCta * 32, 0, stream>>>(A, LIST_8);
+  transform4_kernel<true><<<grid(total / 32 + 1, 8), 256, 0, stream>>>(A, LIST_4Y);
+  transform4_kernel<false><<<grid(total / 64 + 1, 8), 256, 0, stream>>>(A, LIST_4C);
   return cudaGetLastError();
 }
-int transform_launches(int max_log2_tb) { return 3 + (max_log2_tb >= 4 ? 2 : 0) + (max_log2_tb >= 5 ? 2 : 0); }
+int transform_launches(int max_log2_tb) { return 4 + (max_log2_tb >= 4 ? 1 : 0) + (max_log2_tb >= 5 ? 1 : 0); }
 
 }  // namespace dev
 }  // namespace heic
