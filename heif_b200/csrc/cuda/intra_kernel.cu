@@ -42,72 +42,75 @@ struct Ctu {
   int w, h, ctb, ctb4, x_ctb, y_ctb;
   uint8_t* buf[3];   // sample (x, y) relative to the CTU origin at buf[(y + 1) * stride + x + 16], x, y >= -1
   int stride[3];
-  uint8_t* ref;      // reference samples after substitution, s = 0 .. 4n (bottom-left -> corner -> top-right)
-  uint8_t* reff;     // after smoothing
-  int16_t* refa;     // angular reference array, refa[-32 .. 64]
-  uint32_t* dmask;   // reconstructed 4x4 luma blocks of this CTU, bit uy * ctb4 + ux
+  uint8_t* ref;      // reference samples after substitution, s = 0 .. 4n (bottom-left -> corner -> top-right);
+                     // the second block of a chroma pair (or the smoothed luma samples) at ref + kRefSpan
+  uint8_t* refa;     // angular reference array, refa[-32 .. 64]; second block of a pair at refa + kRefaSpan
   int16_t* res[3];   // residuals of this CTU, z-ordered as in the coefficient arena
   uint32_t* tuw;     // tu_map words of this CTU
   int lane;
   int strong_flag;
 };
+constexpr int kRefSpan = 144, kRefaSpan = 104;
 
-// Reconstructed-yet test of the 4x4 luma unit containing luma position (lx, ly) of the current CTU.
-__device__ __forceinline__ bool unit_done(const Ctu& c, int lx, int ly) {
-  const int bit = (ly >> 2) * c.ctb4 + (lx >> 2);
-  return (c.dmask[bit >> 5] >> (bit & 31)) & 1u;
+__device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
+  return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
 }
 
-// Predicts and reconstructs one N x N block of plane `cidx` at (bx, by) (plane samples, CTU-relative).
-// Deliberately one compact, size-generic body with a single call site: the kernel is instruction-fetch bound
-// when this code is replicated per size and per component.
-__device__ __forceinline__ void predict_block(const Ctu& c, int cidx, uint8_t* buf, int stride, int bx, int by, int log2,
-                                              int mode, bool cbf, const int16_t* __restrict__ resid /* shared */) {
-  const int N = 1 << log2, sub = cidx ? 1 : 0, lane = c.lane;
-  const int total = 4 * N;  // positions 0 .. 4N: s < 2N left column bottom-up, s = 2N corner, s > 2N top row
+// Predicts and reconstructs the N x N block at (bx, by) (plane samples, CTU-relative) of one plane, or — `pair` — of
+// the two chroma planes together (same geometry and mode; buffers `buf_delta` and residuals `res_delta` apart), which
+// shares the availability logic and the loop overheads between Cb and Cr.  A lane produces four horizontally adjacent
+// samples per step.  Deliberately one compact, size-generic body with a single call site: the kernel is
+// instruction-fetch bound when this code is replicated per size and per component.
+__device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* buf, int buf_delta, int stride, int bx, int by,
+                                              int log2, int mode, bool cbf_a, bool cbf_b, const int16_t* __restrict__ resid,
+                                              int res_delta) {
+  const int N = 1 << log2, sub = pair ? 1 : 0, lane = c.lane;
+  const int total = 4 * N, cnt = total + 1;  // positions 0 .. 4N: s < 2N left column bottom-up, s = 2N corner, s > 2N top row
   uint8_t* ref = c.ref;
   // ---- 8.4.4.2.2 reference availability (6.4.1) for a single-slice all-intra picture in z-scan order ---------
   // The left column and the top row exist whenever the block is not on the picture border.  The below-left and
   // above-right N samples belong to ONE aligned N x N block each, which is either completely reconstructed or not
-  // started (transform units are atomic in z-order), further cut by the picture / CTB-row limits to a prefix.  So the
+  // started (transform units are atomic in z-order), further cut by the picture limits to a prefix.  So the
   // available samples form one interval [lo, hi] of the scan (bottom-left -> corner -> top-right), and the
   // substitution process ("nearest available sample before, else first one after") is a clamp of s to that interval.
+  // Reconstructed-yet is a comparison of z-order indices at granularity N inside the CTB: for the below-left
+  // neighbour (cx - 1, cy + 1) the highest differing coordinate bit is ctz(cx) in x (where it is smaller) and
+  // ctz(cy + 1) in y (where it is larger), and y wins ties; likewise for the above-right one.  OR-ing the CTB size
+  // in makes the left / upper CTB (always there) and the lower / right CTB (never there) fall out of the same test.
   int lo, hi;
   {
-    const int cs = c.ctb >> sub;
+    const int units = (c.ctb >> sub) >> log2;  // blocks of this size per CTB side
+    const int cx = bx >> log2, cy = by >> log2;
     const int X0 = (c.x_ctb >> sub) + bx, Y0 = (c.y_ctb >> sub) + by;
     const bool left_ok = X0 > 0, top_ok = Y0 > 0;
     int n_bl = 0, n_tr = 0;
-    if (left_ok && by + N < cs && (bx == 0 || unit_done(c, (bx - 1) << sub, (by + N) << sub)))
-      n_bl = min(N, max(0, (c.h >> sub) - (Y0 + N)));
-    if (top_ok && (by == 0 || (bx + N < cs && unit_done(c, (bx + N) << sub, (by - 1) << sub))))
-      n_tr = min(N, max(0, (c.w >> sub) - (X0 + N)));
+    if (left_ok && __ffs(cx | units) > __ffs(cy + 1)) n_bl = min(N, max(0, (c.h >> sub) - (Y0 + N)));
+    if (top_ok && __ffs(cy | units) >= __ffs(cx + 1)) n_tr = min(N, max(0, (c.w >> sub) - (X0 + N)));
     lo = left_ok ? N - n_bl : 2 * N + 1;
     hi = top_ok ? 3 * N + n_tr : 2 * N - 1;  // lo > hi: nothing available -> 1 << (bitDepth - 1)
   }
+  {
+    const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
+    const int n_ref = pair ? 2 * cnt : cnt;
+    const bool none = lo > hi;
 #pragma unroll 1
-  for (int s0 = 0; s0 <= total; s0 += 32) {
-    const int s = s0 + lane;
-    if (s <= total) {
-      int v = 128;
-      if (lo <= hi) {
-        const int src = min(max(s, lo), hi);
-        const int dx = src <= 2 * N ? -1 : src - 2 * N - 1;
-        const int dy = src <= 2 * N ? 2 * N - 1 - src : -1;
-        v = buf[(by + dy + 1) * stride + bx + dx + 16];
-      }
-      ref[s] = (uint8_t)v;
+    for (int s = lane; s < n_ref; s += 32) {
+      const int second = s >= cnt ? 1 : 0, ss = s - second * cnt;
+      const int d = min(max(ss, lo), hi) - 2 * N;  // <= 0: left column (upwards to the corner), > 0: top row
+      const int off = d <= 0 ? -d * stride : d;
+      ref[ss + second * kRefSpan] = none ? (uint8_t)128 : corner[off + second * buf_delta];
     }
   }
   __syncwarp();
   // ---- 8.4.4.2.3: smoothing (luma only in 4:2:0) ---------------------------------------------------
   const uint8_t* R = ref;
-  if (N > 4 && cidx == 0 && mode != 1) {
+  if (N > 4 && !pair && mode != 1) {
     const int min_dist = min(abs(mode - 26), abs(mode - 10));
     const int thr = N == 8 ? 7 : (N == 16 ? 1 : 0);
     if (min_dist > thr) {
       const bool strong = N == 32 && c.strong_flag && abs((int)ref[64] + ref[128] - 2 * ref[96]) < 8 &&
                           abs((int)ref[64] + ref[0] - 2 * ref[32]) < 8;
+      uint8_t* reff = ref + kRefSpan;
 #pragma unroll 1
       for (int s = lane; s <= total; s += 32) {
         int v;
@@ -119,82 +122,112 @@ __device__ __forceinline__ void predict_block(const Ctu& c, int cidx, uint8_t* b
         } else {
           v = (ref[s - 1] + 2 * ref[s] + ref[s + 1] + 2) >> 2;
         }
-        c.reff[s] = (uint8_t)v;
+        reff[s] = (uint8_t)v;
       }
       __syncwarp();
-      R = c.reff;
+      R = reff;
     }
   }
-  // left(i) = p[-1][i - 1], top(i) = p[i - 1][-1]; index 0 is the corner
-#define LEFT(i) ((int)R[2 * N - (i)])
-#define TOP(i) ((int)R[2 * N + (i)])
-  const int pix = N * N;
-  const bool edge = cidx == 0 && N < 32;
+  // left(i) = p[-1][i - 1] = R[2N - i], top(i) = p[i - 1][-1] = R[2N + i]; index 0 is the corner
+  const int quads = (N * N) >> 2;                // steps of four samples per block
+  const int n_items = pair ? 2 * quads : quads;
+  const int lq = log2 - 2;                       // log2 of the quads per row
+  const bool edge = !pair && N < 32;
   uint8_t* out = buf + (by + 1) * stride + bx + 16;
-  if (mode == 0) {  // 8.4.4.2.4 planar
-    const int tr = TOP(1 + N), bl = LEFT(1 + N);
-#pragma unroll 1
-    for (int p = lane; p < pix; p += 32) {
-      const int x = p & (N - 1), y = p >> log2;
-      int v = ((N - 1 - x) * LEFT(1 + y) + (x + 1) * tr + (N - 1 - y) * TOP(1 + x) + (y + 1) * bl + N) >> (log2 + 1);
-      if (cbf) v = clip8(v + (int)resid[p]);
-      out[y * stride + x] = (uint8_t)v;
+  // mode-specific setup
+  int dc_pack = 0;
+  const int angle = kIntraPredAngle[mode];
+  const bool vertical = mode >= 18;
+  if (mode == 1) {  // 8.4.4.2.5 DC: both blocks of a pair summed in one packed reduction (each sum < 2^16)
+    if (lane < N) {
+      dc_pack = (int)R[2 * N - 1 - lane] + R[2 * N + 1 + lane];
+      if (pair) dc_pack += ((int)R[kRefSpan + 2 * N - 1 - lane] + R[kRefSpan + 2 * N + 1 + lane]) << 16;
     }
-  } else if (mode == 1) {  // 8.4.4.2.5 DC
-    int sum = 0;
-    if (lane < N) sum = LEFT(1 + lane) + TOP(1 + lane);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const int dc = (sum + N) >> (log2 + 1);
+    for (int o = 16; o; o >>= 1) dc_pack += __shfl_xor_sync(0xffffffffu, dc_pack, o);
+  } else if (mode >= 2) {  // 8.4.4.2.6 angular: ra[i], i = -N .. 2N
+    const int top_i = angle < 0 ? N : 2 * N;
+    const int dir = vertical ? 1 : -1;
 #pragma unroll 1
-    for (int p = lane; p < pix; p += 32) {
-      const int x = p & (N - 1), y = p >> log2;
-      int v = dc;
-      if (edge) {
-        if (x == 0 && y == 0) v = (LEFT(1) + 2 * dc + TOP(1) + 2) >> 2;
-        else if (y == 0) v = (TOP(1 + x) + 3 * dc + 2) >> 2;
-        else if (x == 0) v = (LEFT(1 + y) + 3 * dc + 2) >> 2;
-      }
-      if (cbf) v = clip8(v + (int)resid[p]);
-      out[y * stride + x] = (uint8_t)v;
-    }
-  } else {  // 8.4.4.2.6 angular
-    const int angle = kIntraPredAngle[mode];
-    const bool vertical = mode >= 18;
-    int16_t* ra = c.refa;  // ra[i], i = -N .. 2N
-    {
-      const int hi = angle < 0 ? N : 2 * N;
+    for (int second = 0; second < (pair ? 2 : 1); second++) {
+      const uint8_t* Rp = R + second * kRefSpan + 2 * N;
+      uint8_t* ra = c.refa + second * kRefaSpan;
 #pragma unroll 1
-      for (int i = lane; i <= hi; i += 32) ra[i] = (int16_t)(vertical ? TOP(i) : LEFT(i));
+      for (int i = lane; i <= top_i; i += 32) ra[i] = Rp[dir * i];
       if (angle < 0) {
         const int last = (N * angle) >> 5;
-        if (last < -1) {
-          const int inv = kInvAngle[mode - 11];
-          const int i = -1 - lane;  // |last| <= N <= 32: one step
-          if (i >= last) {
-            const int k = (i * inv + 128) >> 8;
-            ra[i] = (int16_t)(vertical ? LEFT(k) : TOP(k));
-          }
-        }
+        const int i = -1 - lane;  // |last| <= N <= 32: one step
+        if (last < -1 && i >= last) ra[i] = Rp[-dir * ((i * (int)kInvAngle[mode - 11] + 128) >> 8)];
       }
     }
     __syncwarp();
-    const bool filt_v = edge && mode == 26, filt_h = edge && mode == 10;
-#pragma unroll 1
-    for (int p = lane; p < pix; p += 32) {
-      const int x = p & (N - 1), y = p >> log2;
-      const int j = vertical ? y : x, i = vertical ? x : y;
-      const int t = (j + 1) * angle, idx = t >> 5, fact = t & 31;
-      const int a = ra[i + idx + 1], b = ra[i + idx + 2];  // b is read but unused when fact == 0 (stays inside refa)
-      int v = (((32 - fact) * a + fact * b + 16) >> 5);
-      if (filt_v && x == 0) v = clip8(TOP(1) + ((LEFT(1 + y) - LEFT(0)) >> 1));
-      if (filt_h && y == 0) v = clip8(LEFT(1) + ((TOP(1 + x) - TOP(0)) >> 1));
-      if (cbf) v = clip8(v + (int)resid[p]);
-      out[y * stride + x] = (uint8_t)v;
-    }
   }
-#undef LEFT
-#undef TOP
+#pragma unroll 1
+  for (int q = lane; q < n_items; q += 32) {
+    const int second = q >= quads ? 1 : 0, qq = q - second * quads;
+    const int y = qq >> lq, x0 = (qq & ((1 << lq) - 1)) << 2;
+    const uint8_t* Rp = R + second * kRefSpan + 2 * N;  // Rp[-i] = left(i), Rp[i] = top(i)
+    int v0, v1, v2, v3;
+    if (mode == 0) {  // 8.4.4.2.4 planar
+      const int L = Rp[-1 - y], tr = Rp[1 + N], bl = Rp[-1 - N];
+      const int a = N - 1 - y, base = (N - 1 - x0) * L + (x0 + 1) * tr + (y + 1) * bl + N, step = tr - L, sh = log2 + 1;
+      v0 = (base + a * Rp[1 + x0]) >> sh;
+      v1 = (base + step + a * Rp[2 + x0]) >> sh;
+      v2 = (base + 2 * step + a * Rp[3 + x0]) >> sh;
+      v3 = (base + 3 * step + a * Rp[4 + x0]) >> sh;
+    } else if (mode == 1) {
+      const int dc = (((dc_pack >> (16 * second)) & 0xffff) + N) >> (log2 + 1);
+      v0 = v1 = v2 = v3 = dc;
+      if (edge) {
+        if (y == 0) {
+          v0 = (Rp[1 + x0] + 3 * dc + 2) >> 2;
+          v1 = (Rp[2 + x0] + 3 * dc + 2) >> 2;
+          v2 = (Rp[3 + x0] + 3 * dc + 2) >> 2;
+          v3 = (Rp[4 + x0] + 3 * dc + 2) >> 2;
+          if (x0 == 0) v0 = (Rp[-1] + 2 * dc + Rp[1] + 2) >> 2;
+        } else if (x0 == 0) {
+          v0 = (Rp[-1 - y] + 3 * dc + 2) >> 2;
+        }
+      }
+    } else {
+      const uint8_t* ra = c.refa + second * kRefaSpan;
+      if (vertical) {
+        const int t = (y + 1) * angle, fact = t & 31;
+        const uint8_t* r5 = ra + x0 + (t >> 5) + 1;
+        const int a0 = r5[0], a1 = r5[1], a2 = r5[2], a3 = r5[3], a4 = r5[4];  // a4 unused when fact == 0 (inside refa)
+        v0 = ((32 - fact) * a0 + fact * a1 + 16) >> 5;
+        v1 = ((32 - fact) * a1 + fact * a2 + 16) >> 5;
+        v2 = ((32 - fact) * a2 + fact * a3 + 16) >> 5;
+        v3 = ((32 - fact) * a3 + fact * a4 + 16) >> 5;
+        if (edge && mode == 26 && x0 == 0) v0 = clip8(Rp[1] + ((Rp[-1 - y] - Rp[0]) >> 1));
+      } else {
+        const uint8_t* ry = ra + y + 1;
+        int t = (x0 + 1) * angle;
+        v0 = ((32 - (t & 31)) * ry[t >> 5] + (t & 31) * ry[(t >> 5) + 1] + 16) >> 5;
+        t += angle;
+        v1 = ((32 - (t & 31)) * ry[t >> 5] + (t & 31) * ry[(t >> 5) + 1] + 16) >> 5;
+        t += angle;
+        v2 = ((32 - (t & 31)) * ry[t >> 5] + (t & 31) * ry[(t >> 5) + 1] + 16) >> 5;
+        t += angle;
+        v3 = ((32 - (t & 31)) * ry[t >> 5] + (t & 31) * ry[(t >> 5) + 1] + 16) >> 5;
+        if (edge && mode == 10 && y == 0) {
+          const int l1 = Rp[-1], c0 = Rp[0];
+          v0 = clip8(l1 + ((Rp[1 + x0] - c0) >> 1));
+          v1 = clip8(l1 + ((Rp[2 + x0] - c0) >> 1));
+          v2 = clip8(l1 + ((Rp[3 + x0] - c0) >> 1));
+          v3 = clip8(l1 + ((Rp[4 + x0] - c0) >> 1));
+        }
+      }
+    }
+    if (second ? cbf_b : cbf_a) {
+      const uint2 r = *reinterpret_cast<const uint2*>(resid + second * res_delta + (qq << 2));
+      v0 = clip8(v0 + (int)(int16_t)(r.x & 0xffffu));
+      v1 = clip8(v1 + ((int)r.x >> 16));
+      v2 = clip8(v2 + (int)(int16_t)(r.y & 0xffffu));
+      v3 = clip8(v3 + ((int)r.y >> 16));
+    }
+    *reinterpret_cast<uint32_t*>(out + second * buf_delta + y * stride + x0) = pack4(v0, v1, v2, v3);
+  }
   __syncwarp();
 }
 
@@ -245,14 +278,10 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
     p += (size_t)n4a * 4 * 2;
     c.tuw = reinterpret_cast<uint32_t*>(p);
     p += (size_t)n4a * 4;
-    c.dmask = reinterpret_cast<uint32_t*>(p);
-    p += 32;
     c.ref = p;
-    p += 144;
-    c.reff = p;
-    p += 144;
-    c.refa = reinterpret_cast<int16_t*>(p) + 32;
-    p += 2 * 104;
+    p += 2 * kRefSpan;
+    c.refa = p + 32;
+    p += 2 * kRefaSpan;
     const int sy = 2 * ctb_a + 20, sc = ctb_a + 20;
     c.buf[0] = p;
     c.stride[0] = 2 * c.ctb + 20;
@@ -315,7 +344,6 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
           }
         }
       }
-      if (lane < 8) c.dmask[lane] = 0;
       cp_async_wait_all();
       __syncwarp();
       if (clear_coeff) {
@@ -345,24 +373,17 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
         const int log2 = (int)tu_log2(w), n = 1 << log2;
         const int ux = (int)compact1((uint32_t)idx), uy = (int)compact1((uint32_t)idx >> 1);
         const int bx = ux << 2, by = uy << 2;
-        // luma, then (when this TU carries them) Cb and Cr: one call site keeps the kernel's code small
-        const int n_blk = ((w & TU_HAS_CHROMA) && n_planes == 3) ? 3 : 1;
-        const int log2c = log2 > 2 ? log2 - 1 : 2;
-        const int cbx = (log2 > 2 ? bx : bx - 4) >> 1, cby = (log2 > 2 ? by : by - 4) >> 1;
+        // luma, then (when this TU carries them) Cb and Cr as a pair: one call site keeps the kernel's code small
+        const int n_calls = ((w & TU_HAS_CHROMA) && n_planes == 3) ? 2 : 1;
+        const int buf_delta = (int)(c.buf[2] - c.buf[1]), res_delta = (int)(c.res[2] - c.res[1]);
 #pragma unroll 1
-        for (int k = 0; k < n_blk; k++) {
-          const int16_t* r = k == 0 ? c.res[0] + idx * 16 : (k == 1 ? c.res[1] : c.res[2]) + (idx >> 2) * 16;
-          const bool cbf = (w & (k == 0 ? TU_CBF_Y : (k == 1 ? TU_CBF_CB : TU_CBF_CR))) != 0;
-          predict_block(c, k, k == 0 ? c.buf[0] : (k == 1 ? c.buf[1] : c.buf[2]), k ? c.stride[1] : c.stride[0], k ? cbx : bx,
-                        k ? cby : by, k ? log2c : log2, k ? (int)tu_chroma_mode(w) : (int)tu_luma_mode(w), cbf, r);
-          if (k == 0) {
-            const int b4 = n >> 2;
-            if (lane < b4) {
-              const int bit = (uy + lane) * c.ctb4 + ux;
-              atomicOr(&c.dmask[bit >> 5], ((1u << b4) - 1u) << (bit & 31));
-            }
-            __syncwarp();
-          }
+        for (int k = 0; k < n_calls; k++) {
+          const bool pr = k != 0;
+          predict_block(c, pr, pr ? c.buf[1] : c.buf[0], pr ? buf_delta : 0, pr ? c.stride[1] : c.stride[0],
+                        pr ? (log2 > 2 ? bx : bx - 4) >> 1 : bx, pr ? (log2 > 2 ? by : by - 4) >> 1 : by,
+                        pr ? (log2 > 2 ? log2 - 1 : 2) : log2, pr ? (int)tu_chroma_mode(w) : (int)tu_luma_mode(w),
+                        (w & (pr ? TU_CBF_CB : TU_CBF_Y)) != 0, pr && (w & TU_CBF_CR) != 0,
+                        pr ? c.res[1] + (idx >> 2) * 16 : c.res[0] + idx * 16, pr ? res_delta : 0);
         }
         idx += (n >> 2) * (n >> 2);
       }
@@ -396,7 +417,7 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
 int intra_warp_bytes(int log2_ctb) {
   const int ctb = 1 << log2_ctb, n4 = (ctb >> 2) * (ctb >> 2);
   size_t b = (size_t)n4 * 16 * 2 + 2 * (size_t)n4 * 4 * 2 + (size_t)n4 * 4;  // residuals + tu words
-  b += 32 + 144 + 144 + 2 * 104;
+  b += 2 * kRefSpan + 2 * kRefaSpan;
   b += (size_t)(ctb + 1) * (2 * ctb + 20) + (size_t)2 * (ctb / 2 + 1) * (ctb + 20);
   return (int)((b + 15) & ~(size_t)15);
 }
