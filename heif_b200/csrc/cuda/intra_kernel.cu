@@ -92,13 +92,19 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
   {
     const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
     const int n_ref = pair ? 2 * cnt : cnt;
-    const bool none = lo > hi;
+    const int lo_d = lo - 2 * N, hi_d = hi - 2 * N;  // d <= 0: left column (upwards to the corner), d > 0: top row
+    if (lo > hi) {
+      for (int s = lane; s < 2 * kRefSpan; s += 32) ref[s] = 128;
+    } else {
 #pragma unroll 1
-    for (int s = lane; s < n_ref; s += 32) {
-      const int second = s >= cnt ? 1 : 0, ss = s - second * cnt;
-      const int d = min(max(ss, lo), hi) - 2 * N;  // <= 0: left column (upwards to the corner), > 0: top row
-      const int off = d <= 0 ? -d * stride : d;
-      ref[ss + second * kRefSpan] = none ? (uint8_t)128 : corner[off + second * buf_delta];
+      for (int s = lane - 2 * N; s < n_ref - 2 * N; s += 32) {
+        const bool second = s > 2 * N;
+        const int ss = second ? s - cnt : s;                 // position relative to the corner
+        const int d = min(max(ss, lo_d), hi_d);
+        const uint8_t* src = corner + (d <= 0 ? -d * stride : d);
+        if (second) src += buf_delta;
+        ref[(second ? ss + kRefSpan : ss) + 2 * N] = *src;
+      }
     }
   }
   __syncwarp();
@@ -231,10 +237,18 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
   __syncwarp();
 }
 
+// Byte offsets of a warp's scratch areas (sized for the batch's largest CTB), computed on the host: as kernel
+// parameters they cost one add from the constant bank wherever a pointer is needed again.
+struct IntraLayout {
+  int res1, res2, tuw, ref, refa, buf0, buf1, buf2;
+  int stride_y, stride_c;  // row strides of the CTU buffers
+  int warp_bytes;
+};
+
 #ifndef HEIC_INTRA_MIN_CTAS
 #define HEIC_INTRA_MIN_CTAS 3
 #endif
-__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, int warp_bytes, int log2_ctb_alloc, int clear_coeff) {
+__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, IntraLayout L, int clear_coeff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t tile = order[blockIdx.x];
   const TileParams* tp = A.tiles + tile;
@@ -267,29 +281,18 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
   const int n_planes = pp->chroma ? 3 : 1;
   const int n4sq = c.ctb4 * c.ctb4;
   {
-    // carve this warp's scratch (sized for the batch's largest CTB)
-    unsigned char* p = smem_raw + progress_bytes + (size_t)slot * warp_bytes;
-    const int ctb_a = 1 << log2_ctb_alloc, n4a = (ctb_a >> 2) * (ctb_a >> 2);
+    unsigned char* p = smem_raw + progress_bytes + (size_t)slot * L.warp_bytes;
     c.res[0] = reinterpret_cast<int16_t*>(p);
-    p += (size_t)n4a * 16 * 2;
-    c.res[1] = reinterpret_cast<int16_t*>(p);
-    p += (size_t)n4a * 4 * 2;
-    c.res[2] = reinterpret_cast<int16_t*>(p);
-    p += (size_t)n4a * 4 * 2;
-    c.tuw = reinterpret_cast<uint32_t*>(p);
-    p += (size_t)n4a * 4;
-    c.ref = p;
-    p += 2 * kRefSpan;
-    c.refa = p + 32;
-    p += 2 * kRefaSpan;
-    const int sy = 2 * ctb_a + 20, sc = ctb_a + 20;
-    c.buf[0] = p;
-    c.stride[0] = 2 * c.ctb + 20;
-    p += (size_t)(ctb_a + 1) * sy;
-    c.buf[1] = p;
-    c.stride[1] = c.stride[2] = c.ctb + 20;
-    p += (size_t)(ctb_a / 2 + 1) * sc;
-    c.buf[2] = p;
+    c.res[1] = reinterpret_cast<int16_t*>(p + L.res1);
+    c.res[2] = reinterpret_cast<int16_t*>(p + L.res2);
+    c.tuw = reinterpret_cast<uint32_t*>(p + L.tuw);
+    c.ref = p + L.ref;
+    c.refa = p + L.refa + 32;
+    c.buf[0] = p + L.buf0;
+    c.buf[1] = p + L.buf1;
+    c.buf[2] = p + L.buf2;
+    c.stride[0] = L.stride_y;
+    c.stride[1] = c.stride[2] = L.stride_c;
   }
   const uint32_t* tu_map = A.tu_map + tp->tu_off;
   uint8_t* plane[3] = {A.recon + tp->plane_off[0], A.recon + tp->plane_off[1], A.recon + tp->plane_off[2]};
@@ -414,12 +417,30 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
   }
 }
 
-int intra_warp_bytes(int log2_ctb) {
+IntraLayout intra_layout(int log2_ctb) {
   const int ctb = 1 << log2_ctb, n4 = (ctb >> 2) * (ctb >> 2);
-  size_t b = (size_t)n4 * 16 * 2 + 2 * (size_t)n4 * 4 * 2 + (size_t)n4 * 4;  // residuals + tu words
-  b += 2 * kRefSpan + 2 * kRefaSpan;
-  b += (size_t)(ctb + 1) * (2 * ctb + 20) + (size_t)2 * (ctb / 2 + 1) * (ctb + 20);
-  return (int)((b + 15) & ~(size_t)15);
+  IntraLayout L;
+  int o = n4 * 16 * 2;  // luma residuals first
+  L.res1 = o;
+  o += n4 * 4 * 2;
+  L.res2 = o;
+  o += n4 * 4 * 2;
+  L.tuw = o;
+  o += n4 * 4;
+  L.ref = o;
+  o += 2 * kRefSpan;
+  L.refa = o;
+  o += 2 * kRefaSpan;
+  L.stride_y = 2 * ctb + 20;  // 16 bytes of apron on the left (alignment), the above-right CTU and slack on the right
+  L.stride_c = ctb + 20;
+  L.buf0 = o;
+  o += (ctb + 1) * L.stride_y;
+  L.buf1 = o;
+  o += (ctb / 2 + 1) * L.stride_c;
+  L.buf2 = o;
+  o += (ctb / 2 + 1) * L.stride_c;
+  L.warp_bytes = (o + 15) & ~15;
+  return L;
 }
 
 }  // namespace
@@ -427,15 +448,15 @@ int intra_warp_bytes(int log2_ctb) {
 cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ctb, int max_hctb, int n_slots, bool clear_coeff,
                          cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;
-  const int wb = intra_warp_bytes(max_log2_ctb);
-  const size_t smem = (n_slots > 1 ? (((size_t)max_hctb * 4 + 15) & ~(size_t)15) : 0) + (size_t)n_slots * wb;
+  const IntraLayout L = intra_layout(max_log2_ctb);
+  const size_t smem = (n_slots > 1 ? (((size_t)max_hctb * 4 + 15) & ~(size_t)15) : 0) + (size_t)n_slots * L.warp_bytes;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr = smem;
   }
-  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, wb, max_log2_ctb, clear_coeff ? 1 : 0);
+  intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, L, clear_coeff ? 1 : 0);
   return cudaGetLastError();
 }
 
