@@ -5,6 +5,10 @@
 // There is no CPU fallback: without a usable CUDA device every entry point fails with HEIC_E_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -710,6 +714,11 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
     y_off[i + 1] = y_off[i] + ow * oh;
     c_off[i + 1] = c_off[i] + ((ow + 1) / 2) * ((oh + 1) / 2);
   }
+  static const bool trace = std::getenv("HEIC_B200_TRACE") != nullptr;  // host-side phase times of a submit, to stderr
+  using clk = std::chrono::steady_clock;
+  auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
+  const clk::time_point t_call = clk::now();
+  double t_wait = 0, t_load = 0, t_run = 0;
   auto job = std::make_unique<heic_b200_job>();
   job->ctx = ctx;
   job->n_tiles = first_tile[n_imgs];
@@ -735,12 +744,18 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
       ctx->pipe_batch[slot]->ctx = ctx;
       ctx->pipe_batch[slot]->stream = ctx->pipe_stream[slot];
     }
+    clk::time_point t0 = clk::now();
     harvest_slot(ctx, slot);  // the slot's previous chunk (kernels, copies, status) is complete before its buffers are reused
+    t_wait += ms_since(t0);
     heic_b200_batch* b = ctx->pipe_batch[slot].get();
     cudaStream_t st = b->stream;
     b->apply_transforms = apply_transforms != 0;
+    t0 = clk::now();
     b->load(imgs + i0, cnt, rgb_out != nullptr);
+    t_load += ms_since(t0);
+    t0 = clk::now();
     b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
+    t_run += ms_since(t0);
     if (rgb_out) {
       bool one_copy = image_stride == b->rgb_image_stride && pitch == b->rgb_pitch;
       for (size_t i = 0; i < b->images.size() && one_copy; i++)
@@ -793,6 +808,9 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
       }
     throw;
   }
+  if (trace)
+    std::fprintf(stderr, "[heic_b200] submit %u images: %.1f ms on the host (slot wait %.1f, load %.1f, launch %.1f)\n", n_imgs,
+                 ms_since(t_call), t_wait, t_load, t_run);
   return job.release();
 }
 
