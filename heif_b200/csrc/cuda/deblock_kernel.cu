@@ -41,25 +41,27 @@ struct Pic {
   int w8, log2_ctb, wctb;
 };
 
-// log2 size of the transform unit covering luma sample (x, y): probe the aligned candidate origins.
+// log2 size of the transform unit covering luma sample (x, y): probe the four aligned candidate origins.  The probes
+// are independent loads (no early exit), so they — and those of the cell's other edge segments — are in flight together.
 __device__ __forceinline__ int tu_log2_at(const Pic& p, int x, int y) {
   const int ctb4 = 1 << (p.log2_ctb - 2);
   const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
   const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
   const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
-#pragma unroll
-  for (int l = 0; l < 4; l++) {
-    const uint32_t w = tu[z & ~((1u << (2 * l)) - 1u)];
-    if ((w & TU_ORIGIN) && (int)((w >> 1) & 3u) == l) return l + 2;
-  }
-  return 5;  // not reached for a fully parsed picture
+  const uint32_t w0 = tu[z], w1 = tu[z & ~3u], w2 = tu[z & ~15u], w3 = tu[z & ~63u];
+  int lg = 5;  // a fully parsed picture always matches one of the four
+  if ((w3 & 7u) == (TU_ORIGIN | (3u << 1))) lg = 5;
+  if ((w2 & 7u) == (TU_ORIGIN | (2u << 1))) lg = 4;
+  if ((w1 & 7u) == (TU_ORIGIN | (1u << 1))) lg = 3;
+  if ((w0 & 7u) == (TU_ORIGIN | (0u << 1))) lg = 2;
+  return lg;
 }
 __device__ __forceinline__ int qp_at(const Pic& p, int x, int y) { return p.qp_map[(y >> 3) * p.w8 + (x >> 3)]; }
 
 // Luma edge filter over one 4-line segment held in registers: P(i, l) / Q(i, l) are references.
 // s[l][0..7] = p3 p2 p1 p0 q0 q1 q2 q3 of line l.
-__device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_p, int qp_q, int beta_off2, int tc_off2) {
-  const int qpl = (qp_p + qp_q + 1) >> 1;
+__device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_sum, int beta_off2, int tc_off2) {
+  const int qpl = (qp_sum + 1) >> 1;
   const int beta = kBetaTable[clip3(0, 51, qpl + beta_off2)];
   const int tc = kTcTable[clip3(0, 53, qpl + 2 + tc_off2)];
   const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
@@ -96,8 +98,8 @@ __device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_p, in
   }
 }
 
-__device__ __forceinline__ void filter_chroma_segment(int (&s)[4][8], int qp_p, int qp_q, int c_qp_off, int tc_off2) {
-  const int qpi = ((qp_p + qp_q + 1) >> 1) + c_qp_off;  // cQpPicOffset: PPS offset only (8.7.2.5.5)
+__device__ __forceinline__ void filter_chroma_segment(int (&s)[4][8], int qp_sum, int c_qp_off, int tc_off2) {
+  const int qpi = ((qp_sum + 1) >> 1) + c_qp_off;  // cQpPicOffset: PPS offset only (8.7.2.5.5)
   const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
   const int tc = kTcTable[clip3(0, 53, qpc + 2 + tc_off2)];
   if (!tc) return;
@@ -135,54 +137,61 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
       px[r][4 + i] = (int)((b >> (8 * i)) & 0xffu);
     }
   }
-  bool changed = false;
-  // ---- vertical edge at x = 8k (luma: every 8 samples; chroma 4:2:0: every 8 chroma = 16 luma samples) ----
-  if (has_left && has_right) {
-    const int xl = (8 * k) << SUB;  // luma position of the edge
+  // ---- which of the cell's four edge segments exist, and their QPs: all metadata loads issued before any filtering ----
+  // vertical edge at x = 8k (luma: every 8 samples; chroma 4:2:0: every 8 chroma = 16 luma samples), segments of 4 rows;
+  // horizontal edge at y = 8j, segments of 4 columns
+  const int xe = (8 * k) << SUB, ye = (8 * j) << SUB;  // luma positions of the two edges
+  bool seg_do[4];
+  int seg_qp[4];  // qp_p + qp_q
 #pragma unroll
-    for (int seg = 0; seg < 2; seg++) {
-      if (seg == 0 ? !has_top : !has_bottom) continue;
-      const int yl = (y0 + 4 * seg) << SUB;
+  for (int g = 0; g < 4; g++) {
+    const bool vert = g < 2;
+    const int half = g & 1;
+    bool ok = has_left && has_right && has_top && has_bottom;
+    if (vert) ok = has_left && has_right && (half == 0 ? has_top : has_bottom);
+    else ok = has_top && has_bottom && (half == 0 ? has_left : has_right);
+    const int xl = vert ? xe : (x0 + 4 * half) << SUB, yl = vert ? (y0 + 4 * half) << SUB : ye;
+    seg_do[g] = false;
+    seg_qp[g] = 0;
+    if (ok) {
       const int lg = tu_log2_at(pic, xl, yl);
-      if (xl & ((1 << lg) - 1)) continue;  // not a transform-block edge
-      const int qp_q = qp_at(pic, xl, yl), qp_p = qp_at(pic, xl - 1, yl);
-      int s[4][8];
-#pragma unroll
-      for (int l = 0; l < 4; l++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) s[l][i] = px[4 * seg + l][i];
-      if (CIDX == 0) filter_luma_segment(s, qp_p, qp_q, beta_off2, tc_off2);
-      else filter_chroma_segment(s, qp_p, qp_q, c_qp_off, tc_off2);
-#pragma unroll
-      for (int l = 0; l < 4; l++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) px[4 * seg + l][i] = s[l][i];
-      changed = true;
+      seg_qp[g] = qp_at(pic, xl, yl) + (vert ? qp_at(pic, xl - 1, yl) : qp_at(pic, xl, yl - 1));
+      seg_do[g] = ((vert ? xl : yl) & ((1 << lg) - 1)) == 0;  // a transform-block edge
     }
   }
-  // ---- horizontal edge at y = 8j on the vertically filtered samples ----------------------------------
-  if (has_top && has_bottom) {
-    const int yl = (8 * j) << SUB;
+  bool changed = false;
 #pragma unroll
-    for (int seg = 0; seg < 2; seg++) {
-      if (seg == 0 ? !has_left : !has_right) continue;
-      const int xl = (x0 + 4 * seg) << SUB;
-      const int lg = tu_log2_at(pic, xl, yl);
-      if (yl & ((1 << lg) - 1)) continue;
-      const int qp_q = qp_at(pic, xl, yl), qp_p = qp_at(pic, xl, yl - 1);
-      int s[4][8];
+  for (int seg = 0; seg < 2; seg++) {
+    if (!seg_do[seg]) continue;
+    int s[4][8];
 #pragma unroll
-      for (int l = 0; l < 4; l++)
+    for (int l = 0; l < 4; l++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) s[l][i] = px[i][4 * seg + l];
-      if (CIDX == 0) filter_luma_segment(s, qp_p, qp_q, beta_off2, tc_off2);
-      else filter_chroma_segment(s, qp_p, qp_q, c_qp_off, tc_off2);
+      for (int i = 0; i < 8; i++) s[l][i] = px[4 * seg + l][i];
+    if (CIDX == 0) filter_luma_segment(s, seg_qp[seg], beta_off2, tc_off2);
+    else filter_chroma_segment(s, seg_qp[seg], c_qp_off, tc_off2);
 #pragma unroll
-      for (int l = 0; l < 4; l++)
+    for (int l = 0; l < 4; l++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) px[i][4 * seg + l] = s[l][i];
-      changed = true;
-    }
+      for (int i = 0; i < 8; i++) px[4 * seg + l][i] = s[l][i];
+    changed = true;
+  }
+  // ---- horizontal edge on the vertically filtered samples ----------------------------------
+#pragma unroll
+  for (int seg = 0; seg < 2; seg++) {
+    if (!seg_do[2 + seg]) continue;
+    int s[4][8];
+#pragma unroll
+    for (int l = 0; l < 4; l++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) s[l][i] = px[i][4 * seg + l];
+    if (CIDX == 0) filter_luma_segment(s, seg_qp[2 + seg], beta_off2, tc_off2);
+    else filter_chroma_segment(s, seg_qp[2 + seg], c_qp_off, tc_off2);
+#pragma unroll
+    for (int l = 0; l < 4; l++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) px[i][4 * seg + l] = s[l][i];
+    changed = true;
   }
   if (!changed) return;
 #pragma unroll
