@@ -196,8 +196,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "592")), help="images per GPU per step")
     ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "256")), help="images per reference-facing call")
-    ap.add_argument("--ref-images", type=int, default=16, help="images per step of the CPU arm")
-    ap.add_argument("--cpu-images", type=int, default=32, help="images in the cpu_baseline sample")
+    ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU arm")
+    ap.add_argument("--cpu-images", type=int, default=256, help="images in the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--stages", action="store_true", help="also print a per-stage table to stderr")
     args = ap.parse_args()

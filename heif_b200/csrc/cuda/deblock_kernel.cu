@@ -212,8 +212,11 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
 
 // One launch for luma (KIND 0) and one for the two chroma planes (KIND 1): each launch then runs a single filter body
 // that fits the instruction cache.  grid: flat over (tile, block of cells of the tile), cells numbered row by row.
+#ifndef HEIC_DEBLOCK_MIN_CTAS
+#define HEIC_DEBLOCK_MIN_CTAS 6
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(128, 6) deblock_kernel(Arenas A, uint32_t blocks_per_tile) {
+__global__ void __launch_bounds__(128, HEIC_DEBLOCK_MIN_CTAS) deblock_kernel(Arenas A, uint32_t blocks_per_tile) {
   const uint32_t tile = blockIdx.x / blocks_per_tile;
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
