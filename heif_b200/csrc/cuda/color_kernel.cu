@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.h"
+#include "sao_common.cuh"
 
 namespace heic {
 namespace dev {
@@ -25,11 +26,50 @@ __device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, ui
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+// SAO of one 8 x 2 luma / 4 x 1 chroma half of a thread's block.  Out of line: real streams switch SAO on for a small
+// share of the CTBs, and keeping this code off the main path keeps the conversion loop compact.
+struct HalfBlock {
+  uint2 a, b;        // luma rows ly, ly + 1
+  uint32_t cb, cr;
+};
+struct SaoGeom {
+  uint64_t cb_off, cr_off;
+  int pitch_y, pitch_c, tile_w, tile_h, chroma;
+};
+__device__ __noinline__ HalfBlock sao_half(SaoGeom J, const uint8_t* t, uint32_t lx, uint32_t ly, bool two_rows, uint4 sp, HalfBlock hb) {
+  if (sp.x & 3u) {
+    uint32_t o[2] = {hb.a.x, hb.a.y};
+    sao::sao8(o, t + (size_t)ly * J.pitch_y, (int)lx, (int)ly, (int)J.tile_w, (int)J.tile_h, (int)J.pitch_y, sp.x, (int)(sp.x & 3u));
+    hb.a = make_uint2(o[0], o[1]);
+    if (two_rows) {
+      uint32_t p[2] = {hb.b.x, hb.b.y};
+      sao::sao8(p, t + (size_t)(ly + 1) * J.pitch_y, (int)lx, (int)ly + 1, (int)J.tile_w, (int)J.tile_h, (int)J.pitch_y, sp.x, (int)(sp.x & 3u));
+      hb.b = make_uint2(p[0], p[1]);
+    }
+  }
+  if (J.chroma) {
+    const int cx = (int)(lx >> 1), cy = (int)(ly >> 1), x8 = cx & ~7;  // the aligned group of eight holding our four
+#pragma unroll 1
+    for (int comp = 1; comp <= 2; comp++) {
+      const uint32_t w = comp == 1 ? sp.y : sp.z;
+      if (w & 3u) {
+        const uint8_t* crow = t + (comp == 1 ? J.cb_off : J.cr_off) + (size_t)cy * J.pitch_c;
+        const uint2 c8 = *reinterpret_cast<const uint2*>(crow + x8);
+        uint32_t o[2] = {c8.x, c8.y};
+        sao::sao8(o, crow, x8, cy, (int)(J.tile_w >> 1), (int)(J.tile_h >> 1), (int)J.pitch_c, w, (int)(w & 3u));
+        (comp == 1 ? hb.cb : hb.cr) = o[(cx >> 2) & 1];
+      }
+    }
+  }
+  return hb;
+}
+
 // A thread converts a 16 x 2 block of the canvas (two rows share one row of chroma): 32 + 16 bytes in, 96 bytes out, all as
 // 16-byte accesses.  FULL: full-range input, where (256 Y + t) >> 8 == Y + (t >> 8), so the chroma terms are computed
 // once per 2x2 quad and a pixel costs an add and a clamp per channel.
 // grid: flat over (image, pair of canvas rows, block of 16-pixel groups).
-template <bool FULL>
+// FUSED: the planes are the deblocked reconstruction and SAO is applied here (saves writing and re-reading the final planes).
+template <bool FULL, bool FUSED>
 __global__ void __launch_bounds__(128) color_stitch_kernel(ColorJob J, Coeffs K, uint32_t row_pairs, uint32_t xblocks) {
   const uint32_t per_image = row_pairs * xblocks;
   const uint32_t image = blockIdx.x / per_image, rem = blockIdx.x % per_image;
@@ -45,16 +85,29 @@ __global__ void __launch_bounds__(128) color_stitch_kernel(ColorJob J, Coeffs K,
     const uint32_t xh = x + 8 * h;
     if (xh < J.out_w) {
       const uint32_t tc = xh / J.tile_w, lx = xh - tc * J.tile_w;
-      const uint8_t* t = J.planes + (size_t)(image * J.grid_cols * J.grid_rows + tr * J.grid_cols + tc) * J.tile_stride;
-      const uint2 a = *reinterpret_cast<const uint2*>(t + (size_t)ly * J.pitch_y + lx);
-      const uint2 b = two_rows ? *reinterpret_cast<const uint2*>(t + (size_t)(ly + 1) * J.pitch_y + lx) : make_uint2(0u, 0u);
-      yv[0][2 * h] = a.x, yv[0][2 * h + 1] = a.y, yv[1][2 * h] = b.x, yv[1][2 * h + 1] = b.y;
+      const uint32_t ti = image * J.grid_cols * J.grid_rows + tr * J.grid_cols + tc;
+      const uint8_t* t = J.planes + (size_t)ti * J.tile_stride;
+      uint2 a = *reinterpret_cast<const uint2*>(t + (size_t)ly * J.pitch_y + lx);
+      uint2 b = two_rows ? *reinterpret_cast<const uint2*>(t + (size_t)(ly + 1) * J.pitch_y + lx) : make_uint2(0u, 0u);
       cbv[h] = crv[h] = 0x80808080u;
       if (J.chroma) {
         const size_t co = (size_t)(ly >> 1) * J.pitch_c + (lx >> 1);
         cbv[h] = *reinterpret_cast<const uint32_t*>(t + J.cb_off + co);
         crv[h] = *reinterpret_cast<const uint32_t*>(t + J.cr_off + co);
       }
+      if (FUSED) {
+        // the eight luma samples (both rows: ly is even) and the four chroma samples lie in one CTB; its parameter words
+        // are zero (type 0) for a component whose slice-level SAO flag is off, so one 16-byte load decides everything
+        const uint4 sp = *reinterpret_cast<const uint4*>(J.sao + (size_t)ti * J.sao_stride +
+                                                         (size_t)((ly >> J.log2_ctb) * J.wctb + (lx >> J.log2_ctb)) * 4);
+        if ((sp.x | sp.y | sp.z) & 3u) {
+          HalfBlock hb = {a, b, cbv[h], crv[h]};
+          const SaoGeom g = {J.cb_off, J.cr_off, (int)J.pitch_y, (int)J.pitch_c, (int)J.tile_w, (int)J.tile_h, (int)J.chroma};
+          hb = sao_half(g, t, lx, ly, two_rows, sp, hb);
+          a = hb.a, b = hb.b, cbv[h] = hb.cb, crv[h] = hb.cr;
+        }
+      }
+      yv[0][2 * h] = a.x, yv[0][2 * h + 1] = a.y, yv[1][2 * h] = b.x, yv[1][2 * h + 1] = b.y;
     } else {
       yv[0][2 * h] = yv[0][2 * h + 1] = yv[1][2 * h] = yv[1][2 * h + 1] = 0u;
       cbv[h] = crv[h] = 0x80808080u;
@@ -155,8 +208,14 @@ cudaError_t launch_color(const ColorJob& job, cudaStream_t stream) {
   }
   const uint32_t groups = (job.out_w + 15) / 16;
   const uint32_t xblocks = (groups + 127) / 128, row_pairs = (job.out_h + 1) / 2;
-  if (job.full_range) color_stitch_kernel<true><<<job.n_images * row_pairs * xblocks, 128, 0, stream>>>(job, k, row_pairs, xblocks);
-  else color_stitch_kernel<false><<<job.n_images * row_pairs * xblocks, 128, 0, stream>>>(job, k, row_pairs, xblocks);
+  const unsigned grid = job.n_images * row_pairs * xblocks;
+  if (job.fused) {
+    if (job.full_range) color_stitch_kernel<true, true><<<grid, 128, 0, stream>>>(job, k, row_pairs, xblocks);
+    else color_stitch_kernel<false, true><<<grid, 128, 0, stream>>>(job, k, row_pairs, xblocks);
+  } else {
+    if (job.full_range) color_stitch_kernel<true, false><<<grid, 128, 0, stream>>>(job, k, row_pairs, xblocks);
+    else color_stitch_kernel<false, false><<<grid, 128, 0, stream>>>(job, k, row_pairs, xblocks);
+  }
   return cudaGetLastError();
 }
 

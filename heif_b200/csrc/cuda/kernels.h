@@ -49,6 +49,11 @@ struct ColorJob {
   uint32_t rotation;            // ccw quarter turns applied to the output
   uint8_t* rgb;
   uint64_t pitch, image_stride; // output layout in bytes
+  // fused == 1: `planes` is the deblocked reconstruction and SAO (8.7.3) is applied on the way in
+  uint32_t fused;
+  const uint32_t* sao;          // SAO parameters of the job's first tile (4 words per CTB; all-zero where SAO is off)
+  uint32_t sao_stride;          // words between tiles
+  uint32_t log2_ctb, wctb;
 };
 cudaError_t launch_color(const ColorJob& job, cudaStream_t stream);
 

@@ -111,6 +111,7 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
+  int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
   // decode_grids pipeline: chunks of `pipe_chunk` images rotate over up to kPipe slots, each with its own stream and
   // scratch batch, so the H2D copy, the kernels and the D2H copy of different chunks overlap
   static constexpr int kPipe = 8;
@@ -150,6 +151,7 @@ struct heic_b200_batch {
   uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
   int max_log2_ctb = 4, max_log2_tb = 2, intra_slots = 1, max_hctb = 1;
   uint32_t stages_run = 0;
+  bool final_stale = false;   // SAO ran fused into the colour kernel: the `final` planes were not written (dump_tile refreshes them)
   bool coeff_clean = false;   // the coefficient arena is all-zero (fresh memset, or the last intra stage cleared it)
   PinnedBuf h_bitstream, h_status, h_params;
   size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
@@ -438,10 +440,13 @@ void heic_b200_batch::run(uint32_t mask) {
     CU(launch_deblock(A, max_w, max_h, st));
     ctx->launches += 2;  // luma + chroma
   }
-  if (mask & HEIC_STAGE_SAO) {
+  const bool fuse = ctx->fuse_sao && (mask & HEIC_STAGE_SAO) && (mask & HEIC_STAGE_COLOR) && d_rgb.p;
+  if ((mask & HEIC_STAGE_SAO) && !fuse) {
     CU(launch_sao(A, max_pitch, max_h, st));
+    final_stale = false;
     ctx->launches++;
   }
+  if (fuse) final_stale = true;
   if ((mask & HEIC_STAGE_COLOR) && d_rgb.p) {
     // consecutive images of identical geometry go out in one launch
     size_t i = 0;
@@ -457,7 +462,12 @@ void heic_b200_batch::run(uint32_t mask) {
       const PicParams& pp = pics[im.pic];
       const TileParams& t0 = tiles[im.first_tile];
       ColorJob job;
-      job.planes = (const uint8_t*)d_final.p + t0.plane_off[0];
+      job.planes = (const uint8_t*)(fuse ? d_recon.p : d_final.p) + t0.plane_off[0];
+      job.fused = fuse ? 1u : 0u;
+      job.sao = A.sao + t0.sao_off;
+      job.sao_stride = (uint32_t)((size_t)pp.wctb * pp.hctb * 4);
+      job.log2_ctb = (uint32_t)pp.log2_ctb;
+      job.wctb = (uint32_t)pp.wctb;
       job.tile_stride = im.n_tiles > 1 || j - i > 1
                             ? (size_t)(tiles[std::min<size_t>(im.first_tile + 1, tiles.size() - 1)].plane_off[0] - t0.plane_off[0])
                             : 0;
@@ -536,6 +546,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_group_factor = std::max(1, env_int("HEIC_B200_CABAC_GROUP_FACTOR", 1));
     c->pipe_chunk = std::max(1, env_int("HEIC_B200_PIPE_CHUNK", 32));
     c->low_latency_tiles = env_int("HEIC_B200_LOW_LATENCY_TILES", 384);
+    c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;
@@ -660,6 +671,11 @@ int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_
       const size_t n = (size_t)pp.wctb * pp.hctb * 4;
       if (dump->sao_len < n) bail(HEIC_E_INVALID_ARG, "sao buffer too small");
       CU(cudaMemcpy(dump->sao, (const uint32_t*)b->d_sao.p + tp.sao_off, n * 4, cudaMemcpyDeviceToHost));
+    }
+    if ((b->stages_run & HEIC_STAGE_SAO) && b->final_stale) {  // SAO was applied inside the colour kernel: write the planes now
+      CU(launch_sao(b->arenas(), b->max_pitch, b->max_h, b->stream));
+      CU(cudaStreamSynchronize(b->stream));
+      b->final_stale = false;
     }
     const uint8_t* src = (const uint8_t*)((b->stages_run & HEIC_STAGE_SAO) ? b->d_final.p : b->d_recon.p);
     for (int c = 0; c < (pp.chroma ? 3 : 1); c++)
@@ -893,6 +909,10 @@ int32_t heic_b200_color_stitch(heic_b200_ctx* ctx, const void* dev_planes, uint3
     CU(cudaSetDevice(ctx->device));
     ColorJob job;
     job.planes = (const uint8_t*)dev_planes;
+    job.fused = 0;
+    job.sao = nullptr;
+    job.sao_stride = 0;
+    job.log2_ctb = job.wctb = 0;
     job.tile_stride = (size_t)tile_w * tile_h * 3 / 2;
     job.cb_off = (size_t)tile_w * tile_h;
     job.cr_off = job.cb_off + (size_t)(tile_w / 2) * (tile_h / 2);
