@@ -20,7 +20,7 @@ from ._capi import HeicError, STAGE_ALL, STAGE_CABAC, STAGE_COLOR, STAGE_DEBLOCK
 
 __all__ = [
     "HeicDecoder", "HeicFile", "HeifReader", "Batch", "HeicError", "remove_emulation_prevention", "parse_sps", "parse_pps",
-    "parse_slice_header", "read_ue", "read_se", "STAGE_ALL", "STAGE_CABAC", "STAGE_TRANSFORM", "STAGE_INTRA", "STAGE_DEBLOCK", "STAGE_SAO",
+    "parse_slice_header", "parse_slice_header_raw", "read_ue", "read_se", "STAGE_ALL", "STAGE_CABAC", "STAGE_TRANSFORM", "STAGE_INTRA", "STAGE_DEBLOCK", "STAGE_SAO",
     "STAGE_COLOR",
 ]
 
@@ -81,6 +81,14 @@ def parse_slice_header(rbsp: bytes, nal_unit_type: int, sps: K.Sps, pps: K.Pps, 
     return out
 
 
+def parse_slice_header_raw(nal_payload: bytes, nal_unit_type: int, sps: K.Sps, pps: K.Pps) -> K.SliceHeader:
+    """The slice header read from a raw NAL payload; offsets stay in raw byte counts (TileDesc.escaped = 1)."""
+    out = K.SliceHeader()
+    K.check(_lib().heic_b200_parse_slice_header_raw(bytes(nal_payload), len(nal_payload), nal_unit_type, C.byref(sps), C.byref(pps),
+                                                    C.byref(out)))
+    return out
+
+
 class HeicFile:
     """A parsed HEIC file: HeifReader::read + the item walk of HeicDecoder::decode up to the slice headers."""
 
@@ -109,6 +117,16 @@ class HeicFile:
     def aux_images(self):
         n = self._lib.heic_b200_file_aux_image_count(self._h)
         return [self._lib.heic_b200_file_aux_image(self._h, i).contents for i in range(n)]
+
+    @property
+    def primary_raw(self) -> K.ImageDesc:
+        """The primary image with raw tile payloads: emulation prevention removal happens on the GPU."""
+        return self._lib.heic_b200_file_primary_image_raw(self._h).contents
+
+    @property
+    def aux_images_raw(self):
+        n = self._lib.heic_b200_file_aux_image_count(self._h)
+        return [self._lib.heic_b200_file_aux_image_raw(self._h, i).contents for i in range(n)]
 
     @property
     def info(self) -> K.FileInfo:
@@ -308,6 +326,17 @@ class HeicDecoder:
         K.check(self._lib.heic_b200_decode_grids_submit(self._h, arr, len(images), out.ctypes.data, out.strides[1], out.strides[0],
                                                         1 if apply_transforms else 0, st, C.byref(job)))
         return (job, st, out)
+
+    def unescape(self, nal_payload: bytes, data_offset: int = 0, substream_offsets=()):
+        """GPU emulation-prevention removal of one raw NAL payload -> (rbsp, data_offset, substream_offsets) re-based."""
+        n = len(substream_offsets)
+        sub = (K.u32 * max(n, 1))(*substream_offsets)
+        sub_out = (K.u32 * max(n, 1))()
+        out = (K.u8 * max(len(nal_payload), 1))()
+        out_len, off = C.c_size_t(), K.u32()
+        K.check(self._lib.heic_b200_unescape(self._h, bytes(nal_payload), len(nal_payload), data_offset, sub, n, out, C.byref(out_len),
+                                             C.byref(off), sub_out))
+        return bytes(out[: out_len.value]), off.value, list(sub_out[:n])
 
     def wait_job(self, job) -> np.ndarray:
         h, st, out = job

@@ -97,7 +97,7 @@ class SliceHeader(C.Structure):
 
 
 class TileDesc(C.Structure):
-    _fields_ = [("rbsp", C.POINTER(u8)), ("rbsp_len", u32), ("nal_unit_type", u32), ("header", SliceHeader)]
+    _fields_ = [("rbsp", C.POINTER(u8)), ("rbsp_len", u32), ("nal_unit_type", u32), ("escaped", u32), ("header", SliceHeader)]
 
 
 class ImageDesc(C.Structure):
@@ -148,14 +148,20 @@ SYMBOLS = [
     ("heic_b200_parse_pps", i32, [C.c_char_p, _sz, C.POINTER(Pps)]),
     ("heic_b200_parse_slice_header", i32,
      [C.c_char_p, _sz, u32, C.POINTER(Sps), C.POINTER(Pps), C.POINTER(u32), _sz, C.POINTER(SliceHeader)]),
+    ("heic_b200_parse_slice_header_raw", i32,
+     [C.c_char_p, _sz, u32, C.POINTER(Sps), C.POINTER(Pps), C.POINTER(SliceHeader)]),
     ("heic_b200_file_open", i32, [C.c_char_p, _sz, C.POINTER(_vp)]),
     ("heic_b200_file_close", None, [_vp]),
     ("heic_b200_file_primary_image", C.POINTER(ImageDesc), [_vp]),
     ("heic_b200_file_aux_image_count", u32, [_vp]),
     ("heic_b200_file_aux_image", C.POINTER(ImageDesc), [_vp, u32]),
+    ("heic_b200_file_primary_image_raw", C.POINTER(ImageDesc), [_vp]),
+    ("heic_b200_file_aux_image_raw", C.POINTER(ImageDesc), [_vp, u32]),
     ("heic_b200_file_parameter_set_nal", i32, [_vp, i32, u32, C.POINTER(C.POINTER(u8)), C.POINTER(_sz)]),
     ("heic_b200_file_tile_nal", i32, [_vp, i32, u32, C.POINTER(C.POINTER(u8)), C.POINTER(_sz)]),
     ("heic_b200_file_info", i32, [_vp, C.POINTER(FileInfo)]),
+    ("heic_b200_unescape", i32,
+     [_vp, C.c_char_p, _sz, u32, C.POINTER(u32), u32, C.POINTER(u8), C.POINTER(_sz), C.POINTER(u32), C.POINTER(u32)]),
     ("heic_b200_decode_grids", i32,
      [_vp, C.POINTER(ImageDesc), u32, _vp, _sz, _sz, i32, C.POINTER(TileStatus)]),
     ("heic_b200_decode_grids_submit", i32,

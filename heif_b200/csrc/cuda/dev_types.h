@@ -90,6 +90,10 @@ struct TileParams {
   uint32_t image, tile_in_image;
   uint32_t bs_off, bs_len;      // un-escaped slice RBSP in the bitstream arena
   uint32_t data_off;            // slice_segment_data() start, relative to bs_off
+  // escaped != 0: the host shipped the raw NAL payload (emulation prevention bytes in place) to raw_off in the raw
+  // arena; bs_len, data_off and the tile's substream offsets count raw bytes until unescape_kernel has rewritten them
+  uint32_t escaped;
+  uint64_t raw_off;
   uint32_t sub_first, n_sub;    // substream start offsets (relative to data_off) in the substream array
   int32_t slice_qp;
   int32_t slice_cb_qp_offset, slice_cr_qp_offset;
@@ -120,6 +124,7 @@ struct TileStatusDev {
 // Arena base pointers of a resident batch.
 struct Arenas {
   const uint8_t* bitstream;
+  const uint8_t* raw;            // raw NAL payloads of the tiles with TileParams::escaped
   const uint32_t* substreams;
   const PicParams* pics;
   const TileParams* tiles;

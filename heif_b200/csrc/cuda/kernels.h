@@ -17,6 +17,9 @@ cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t*
                          int tiles_per_cta, int n_slots, cudaStream_t stream);
 
 // Stage 2 — scaling (8.6.4.2) + inverse DST/DCT (8.6.4.2), in place on the coefficient arena.
+// Emulation-prevention removal (7.4.2 / rbsp_reader.rs:11-39) and entry-point re-basing for the tiles shipped raw:
+// raw arena -> bitstream arena, and bs_len / data_off / substream offsets rewritten in un-escaped bytes.
+cudaError_t launch_unescape(const Arenas& A, TileParams* tiles, uint32_t* substreams, cudaStream_t stream);
 cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_log2_tb, int n_sm, cudaStream_t stream);
 // element offsets of the per-class coded-block lists for `total_tu` tu_map entries; returns the total element count
 size_t transform_list_layout(size_t total_tu, uint32_t off[LIST_CLASSES]);

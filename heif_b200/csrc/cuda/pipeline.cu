@@ -146,6 +146,8 @@ struct heic_b200_batch {
   std::vector<ImageInfo> images;
   std::vector<uint32_t> substreams, order, heavy_first;
   std::vector<CabacClass> classes;
+  size_t raw_bytes = 0;       // raw NAL payloads of the tiles shipped with emulation prevention bytes in place
+  bool any_plain = false;
   size_t bs_bytes = 0, tu_words = 0, coeff_elems = 0, plane_bytes = 0, map4_bytes = 0, map8_bytes = 0, sao_words = 0, wpp_bytes = 0;
   size_t rgb_pitch = 0, rgb_image_stride = 0;
   uint32_t max_tu = 0, max_w = 0, max_h = 0, max_pitch = 0;
@@ -156,11 +158,13 @@ struct heic_b200_batch {
   PinnedBuf h_bitstream, h_status, h_params;
   size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
   DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
-      d_qp, d_sao, d_wpp, d_status, d_rgb, d_list, d_list_count;
+      d_qp, d_sao, d_wpp, d_status, d_rgb, d_list, d_list_count, d_raw;
+  PinnedBuf h_raw;
   uint32_t list_off[LIST_CLASSES] = {};
   Arenas arenas() const {
     Arenas a;
     a.bitstream = (const uint8_t*)d_bitstream.p;
+    a.raw = (const uint8_t*)d_raw.p;
     const uint8_t* pb = (const uint8_t*)d_params.p;
     a.substreams = (const uint32_t*)(pb + off_sub);
     a.pics = (const PicParams*)(pb + off_pics);
@@ -205,6 +209,8 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   order.clear();
   heavy_first.clear();
   classes.clear();
+  raw_bytes = 0;
+  any_plain = false;
   bs_bytes = tu_words = coeff_elems = plane_bytes = map4_bytes = map8_bytes = sao_words = wpp_bytes = 0;
   max_tu = max_w = max_h = max_pitch = 0;
   max_log2_ctb = 4;
@@ -259,6 +265,13 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       tp.tile_in_image = t;
       tp.bs_off = (uint32_t)bs_bytes;
       bs_bytes = up(bs_bytes + tp.bs_len + 8, 16);
+      tp.escaped = im.tiles[t].escaped ? 1u : 0u;
+      if (tp.escaped) {
+        tp.raw_off = raw_bytes;
+        raw_bytes = up(raw_bytes + tp.bs_len + 8, 16);
+      } else {
+        any_plain = true;
+      }
       if (bs_bytes > 0xfff00000ull) bail(HEIC_E_UNSUPPORTED, "more than 4 GiB of slice data in one batch");
       tp.sub_first = (uint32_t)substreams.size();
       for (uint32_t k = 0; k < tp.n_sub; k++) substreams.push_back(im.tiles[t].header.substream_offset[k]);
@@ -355,14 +368,22 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
 
   // ---- device memory + uploads: one pinned blob for all parameter tables, one for the slice data ------------------
   cudaStream_t st = stream;
-  h_bitstream.ensure(bs_bytes + 16);
+  if (any_plain) h_bitstream.ensure(bs_bytes + 16);
+  if (raw_bytes) h_raw.ensure(raw_bytes + 16);
   {
     size_t t = 0;
     uint8_t* hb = (uint8_t*)h_bitstream.p;
+    uint8_t* hr = (uint8_t*)h_raw.p;
     for (uint32_t i = 0; i < n_imgs; i++)
       for (uint32_t k = 0; k < imgs[i].n_tiles; k++, t++) {
-        std::memcpy(hb + tiles[t].bs_off, imgs[i].tiles[k].rbsp, imgs[i].tiles[k].rbsp_len);
-        const size_t end = tiles[t].bs_off + imgs[i].tiles[k].rbsp_len;
+        const size_t len = imgs[i].tiles[k].rbsp_len;
+        if (tiles[t].escaped) {  // raw NAL payload: un-escaped on the device into its bitstream slot
+          std::memcpy(hr + tiles[t].raw_off, imgs[i].tiles[k].rbsp, len);
+          std::memset(hr + tiles[t].raw_off + len, 0, up(len + 8, 16) - len);
+          continue;
+        }
+        std::memcpy(hb + tiles[t].bs_off, imgs[i].tiles[k].rbsp, len);
+        const size_t end = tiles[t].bs_off + len;
         const size_t next = t + 1 < tiles.size() ? tiles[t + 1].bs_off : bs_bytes + 16;
         std::memset(hb + end, 0, next - end);
       }
@@ -402,7 +423,9 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   d_status.ensure(tiles.size() * sizeof(TileStatusDev));
   h_status.ensure(tiles.size() * sizeof(TileStatusDev));
   if (with_rgb) d_rgb.ensure(rgb_image_stride * images.size());
-  CU(cudaMemcpyAsync(d_bitstream.p, h_bitstream.p, bs_bytes + 16, cudaMemcpyHostToDevice, st));
+  d_raw.ensure(raw_bytes ? raw_bytes + 16 : 0);
+  if (any_plain) CU(cudaMemcpyAsync(d_bitstream.p, h_bitstream.p, bs_bytes + 16, cudaMemcpyHostToDevice, st));
+  if (raw_bytes) CU(cudaMemcpyAsync(d_raw.p, h_raw.p, raw_bytes + 16, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(d_params.p, h_params.p, params_bytes, cudaMemcpyHostToDevice, st));
 }
 
@@ -418,6 +441,11 @@ void heic_b200_batch::run(uint32_t mask) {
     coeff_clean = false;
     CU(cudaMemsetAsync(d_status.p, 0, tiles.size() * sizeof(TileStatusDev), st));
     CU(cudaMemsetAsync(d_sao.p, 0, sao_words * 4, st));  // slices without SAO parse no parameters
+    if (raw_bytes) {  // tiles shipped raw: emulation-prevention removal + entry-point re-basing (a no-op once done)
+      uint8_t* pb = (uint8_t*)d_params.p;
+      CU(launch_unescape(A, (TileParams*)(pb + off_tiles), (uint32_t*)(pb + off_sub), st));
+      ctx->launches++;
+    }
     for (const CabacClass& c : classes) {
       CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, tiles_per_cta,
                       c.n_slots, st));
@@ -893,6 +921,56 @@ int32_t heic_b200_decode_file(heic_b200_ctx* ctx, const uint8_t* data, size_t le
     std::unique_ptr<HeicFile> f = HeicDecoder::open(data, len);
     return decode_grids_impl(ctx, &f->primary.desc, 1, rgb_out, pitch, 0, apply_transforms, nullptr, nullptr, nullptr,
                              nullptr);
+  }));
+}
+
+// Stand-alone emulation-prevention removal + entry-point re-basing of one raw NAL payload on the GPU (the stage
+// decode_grids runs for heic_tile_desc::escaped tiles): the device twin of heic_b200_remove_emulation_prevention.
+int32_t heic_b200_unescape(heic_b200_ctx* ctx, const uint8_t* nal_payload, size_t len, uint32_t slice_data_byte_offset,
+                           const uint32_t* substream_offset, uint32_t n_substreams, uint8_t* rbsp_out, size_t* rbsp_len,
+                           uint32_t* slice_data_byte_offset_out, uint32_t* substream_offset_out) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!ctx || !nal_payload || !rbsp_out || !rbsp_len || (n_substreams && (!substream_offset || !substream_offset_out)))
+      bail(HEIC_E_INVALID_ARG, "null argument");
+    if (len > 0x7fffffffu || slice_data_byte_offset > len) bail(HEIC_E_INVALID_ARG, "payload too large or data offset outside it");
+    CU(cudaSetDevice(ctx->device));
+    const size_t padded = up(len + 8, 16) + 16;
+    DevBuf d_raw, d_out, d_tile, d_sub, d_status;
+    d_raw.ensure(padded);
+    d_out.ensure(padded);
+    d_tile.ensure(sizeof(TileParams));
+    d_sub.ensure((size_t)std::max(1u, n_substreams) * 4);
+    d_status.ensure(sizeof(TileStatusDev));
+    TileParams tp;
+    std::memset(&tp, 0, sizeof tp);
+    tp.bs_len = (uint32_t)len;
+    tp.data_off = slice_data_byte_offset;
+    tp.n_sub = n_substreams;
+    tp.escaped = 1;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemsetAsync(d_raw.p, 0, padded, st));
+    CU(cudaMemsetAsync(d_status.p, 0, sizeof(TileStatusDev), st));
+    CU(cudaMemcpyAsync(d_raw.p, nal_payload, len, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_tile.p, &tp, sizeof tp, cudaMemcpyHostToDevice, st));
+    if (n_substreams) CU(cudaMemcpyAsync(d_sub.p, substream_offset, (size_t)n_substreams * 4, cudaMemcpyHostToDevice, st));
+    Arenas A;
+    std::memset(&A, 0, sizeof A);
+    A.raw = (const uint8_t*)d_raw.p;
+    A.bitstream = (const uint8_t*)d_out.p;
+    A.status = (TileStatusDev*)d_status.p;
+    A.n_tiles = 1;
+    CU(launch_unescape(A, (TileParams*)d_tile.p, (uint32_t*)d_sub.p, st));
+    ctx->launches++;
+    TileStatusDev sd;
+    CU(cudaMemcpyAsync(&tp, d_tile.p, sizeof tp, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(&sd, d_status.p, sizeof sd, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (sd.code != 0) bail(HEIC_E_BITSTREAM, "more emulation prevention bytes in one NAL unit than the GPU path handles");
+    *rbsp_len = tp.bs_len;
+    if (slice_data_byte_offset_out) *slice_data_byte_offset_out = tp.data_off;
+    CU(cudaMemcpy(rbsp_out, d_out.p, tp.bs_len, cudaMemcpyDeviceToHost));
+    if (n_substreams) CU(cudaMemcpy(substream_offset_out, d_sub.p, (size_t)n_substreams * 4, cudaMemcpyDeviceToHost));
+    return 0;
   }));
 }
 

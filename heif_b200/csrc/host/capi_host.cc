@@ -81,6 +81,15 @@ int32_t heic_b200_parse_slice_header(const uint8_t* rbsp, size_t len, uint32_t n
   }));
 }
 
+int32_t heic_b200_parse_slice_header_raw(const uint8_t* nal_payload, size_t len, uint32_t nal_unit_type, const heic_sps* sps,
+                                         const heic_pps* pps, heic_slice_header* out) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!nal_payload || !sps || !pps || !out) bail(HEIC_E_INVALID_ARG, "null argument");
+    *out = slice_segment_header_raw(nal_payload, len, nal_unit_type, *sps, *pps);
+    return 0;
+  }));
+}
+
 int32_t heic_b200_file_open(const uint8_t* data, size_t len, heic_b200_file** out) {
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!data || !out) bail(HEIC_E_INVALID_ARG, "null argument");
@@ -101,6 +110,12 @@ uint32_t heic_b200_file_aux_image_count(const heic_b200_file* f) {
 }
 const heic_image_desc* heic_b200_file_aux_image(const heic_b200_file* f, uint32_t i) {
   return (f && i < f->f->aux.size()) ? &f->f->aux[i]->desc : nullptr;
+}
+const heic_image_desc* heic_b200_file_primary_image_raw(const heic_b200_file* f) {
+  return f ? &f->f->primary.desc_raw : nullptr;
+}
+const heic_image_desc* heic_b200_file_aux_image_raw(const heic_b200_file* f, uint32_t i) {
+  return (f && i < f->f->aux.size()) ? &f->f->aux[i]->desc_raw : nullptr;
 }
 static const ImageStorage* image_of(const heic_b200_file* f, int32_t image) {
   if (!f) return nullptr;

@@ -99,6 +99,7 @@ void HeicDecoder::build_image(const HeifReader& reader, const Heif& heif, uint32
   out.rbsp.resize(tile_ids.size());
   out.nal.resize(tile_ids.size());
   out.tiles.resize(tile_ids.size());
+  out.tiles_raw.resize(tile_ids.size());
   for (size_t t = 0; t < tile_ids.size(); ++t) {
     std::vector<uint8_t> item = reader.get_item_data(heif, tile_ids[t]);
     uint16_t header = 0;
@@ -110,6 +111,14 @@ void HeicDecoder::build_image(const HeifReader& reader, const Heif& heif, uint32
     td.rbsp = out.rbsp[t].data();
     td.rbsp_len = static_cast<uint32_t>(out.rbsp[t].size());
     td.header = slice_segment_header(td.rbsp, td.rbsp_len, td.nal_unit_type, sps, out.desc.pps, epb.data(), epb.size());
+    // the same tile as it lies in mdat: raw payload after the 2-byte NAL header, offsets in raw byte counts
+    heic_tile_desc& tr = out.tiles_raw[t];
+    std::memset(&tr, 0, sizeof tr);
+    tr.nal_unit_type = td.nal_unit_type;
+    tr.escaped = 1;
+    tr.rbsp = out.nal[t].data() + 2;
+    tr.rbsp_len = static_cast<uint32_t>(out.nal[t].size() - 2);
+    tr.header = slice_segment_header_raw(tr.rbsp, tr.rbsp_len, tr.nal_unit_type, sps, out.desc.pps);
   }
 
   uint32_t sub_w = (sps.chroma_format_idc == 1 || sps.chroma_format_idc == 2) ? 2 : 1;
@@ -131,6 +140,8 @@ void HeicDecoder::build_image(const HeifReader& reader, const Heif& heif, uint32
   out.desc.rotation_ccw_quarter_turns = irot ? irot->irot_angle : 0;
   out.desc.n_tiles = static_cast<uint32_t>(tile_ids.size());
   out.desc.tiles = out.tiles.data();
+  out.desc_raw = out.desc;
+  out.desc_raw.tiles = out.tiles_raw.data();
 }
 
 std::unique_ptr<HeicFile> HeicDecoder::open(const uint8_t* data, size_t len) {

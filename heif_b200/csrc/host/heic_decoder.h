@@ -14,6 +14,8 @@ namespace heic {
 struct ImageStorage {
   heic_image_desc desc;
   std::vector<heic_tile_desc> tiles;
+  heic_image_desc desc_raw;                // the same image with raw tile payloads (heic_tile_desc::escaped = 1)
+  std::vector<heic_tile_desc> tiles_raw;
   std::vector<std::vector<uint8_t>> rbsp;  // un-escaped slice RBSP per tile (owned)
   std::vector<std::vector<uint8_t>> nal;   // escaped VCL NAL unit per tile incl. 2-byte header
   std::vector<uint8_t> vps_nal, sps_nal, pps_nal;  // escaped parameter-set NAL units from hvcC

@@ -385,7 +385,7 @@ static bool is_idr(uint32_t t) { return t == 19 || t == 20; }
 // assert!/unimplemented! (slice.rs:60-63,106-108).
 heic_slice_header slice_segment_header(const uint8_t* rbsp, size_t len, uint32_t nal_unit_type,
                                        const heic_sps& sps, const heic_pps& pps,
-                                       const uint32_t* epb_pos, size_t n_epb) {
+                                       const uint32_t* epb_pos, size_t n_epb, bool raw_offsets) {
   RbspReader r(rbsp, len);
   heic_slice_header h;
   std::memset(&h, 0, sizeof h);
@@ -445,6 +445,23 @@ heic_slice_header slice_segment_header(const uint8_t* rbsp, size_t len, uint32_t
   ensure(qp >= 0 && qp <= 51, HEIC_E_BITSTREAM, "SliceQpY out of range");
 
   h.slice_data_byte_offset = static_cast<uint32_t>(r.byte_position());
+  if (raw_offsets) {
+    // keep everything in raw (escaped) byte counts: the GPU removes the emulation prevention bytes and re-bases
+    uint64_t e = h.slice_data_byte_offset;
+    for (size_t i = 0; i < n_epb; ++i) {
+      if (epb_pos[i] <= e) ++e;
+      else break;
+    }
+    h.slice_data_byte_offset = static_cast<uint32_t>(e);
+    h.substream_offset[0] = 0;
+    uint64_t sum = 0;
+    for (uint32_t k = 0; k < h.num_entry_point_offsets; ++k) {
+      sum += uint64_t{h.entry_point_offset_minus1[k]} + 1;
+      if (sum > 0xffffffffull) bail(HEIC_E_BITSTREAM, "entry point beyond slice data");
+      h.substream_offset[k + 1] = static_cast<uint32_t>(sum);
+    }
+    return h;
+  }
   // Entry points count bytes of the ESCAPED NAL (7.4.7.1).  Map: un-escaped u -> escaped e, then
   // boundaries back to un-escaped positions.  epb_pos are positions in the escaped payload.
   uint64_t e = h.slice_data_byte_offset;
@@ -464,6 +481,16 @@ heic_slice_header slice_segment_header(const uint8_t* rbsp, size_t len, uint32_t
       bail(HEIC_E_BITSTREAM, "entry points not monotonic");
   }
   return h;
+}
+
+heic_slice_header slice_segment_header_raw(const uint8_t* nal_payload, size_t len, uint32_t nal_unit_type,
+                                           const heic_sps& sps, const heic_pps& pps) {
+  // the header is a few dozen bytes (4 per entry point at most): un-escape a bounded prefix only
+  const size_t prefix = std::min<size_t>(len, 64 + 5 * static_cast<size_t>(HEIC_MAX_ENTRY_POINTS));
+  std::vector<uint32_t> epb;
+  std::vector<uint8_t> head = RbspReader::remove_emulation_prevention(nal_payload, prefix, &epb);
+  // a 00 00 03 cut by the prefix end is not a removal candidate the full scan would agree on; the header ends well before
+  return slice_segment_header(head.data(), head.size(), nal_unit_type, sps, pps, epb.data(), epb.size(), true);
 }
 
 }  // namespace heic

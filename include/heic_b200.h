@@ -158,6 +158,13 @@ typedef struct heic_tile_desc {
   const uint8_t* rbsp;        /* un-escaped slice-segment RBSP (after the 2-byte NAL header), host memory */
   uint32_t rbsp_len;
   uint32_t nal_unit_type;     /* must be an IRAP type; the reference insists on IDR_N_LP (decoder.rs:109-112) */
+  /* [+] 0: `rbsp` is the un-escaped RBSP (what RbspReader::remove_emulation_prevention returns, rbsp_reader.rs:11-39)
+   *        and the header's offsets count un-escaped bytes;
+   *     1: `rbsp` is the raw NAL payload, emulation prevention bytes still in place, and header.slice_data_byte_offset /
+   *        header.substream_offset[] count raw bytes (the way entry_point_offset_minus1 does, 7.4.7.1) — see
+   *        heic_b200_parse_slice_header_raw.  The library then removes the emulation prevention bytes and re-bases
+   *        the offsets on the GPU, and the host never touches the slice data. */
+  uint32_t escaped;
   heic_slice_header header;
 } heic_tile_desc;
 
@@ -211,6 +218,12 @@ int32_t heic_b200_parse_pps(const uint8_t* rbsp, size_t len, heic_pps* out);
 int32_t heic_b200_parse_slice_header(const uint8_t* rbsp, size_t len, uint32_t nal_unit_type,
                                      const heic_sps* sps, const heic_pps* pps,
                                      const uint32_t* epb_pos, size_t n_epb, heic_slice_header* out);
+/* [+] The same header read straight from a raw NAL payload (emulation prevention bytes in place; only the first
+ * bytes are un-escaped, the slice data is not touched): slice_data_byte_offset is the raw position of
+ * slice_segment_data() and substream_offset[k] the running sum of entry_point_offset_minus1 + 1, i.e. raw byte counts.
+ * For heic_tile_desc::escaped = 1. */
+int32_t heic_b200_parse_slice_header_raw(const uint8_t* nal_payload, size_t len, uint32_t nal_unit_type,
+                                         const heic_sps* sps, const heic_pps* pps, heic_slice_header* out);
 
 /* HeifReader::{new, read, get_item_data} + HeicDecoder::decode's item walk
  *                                                               src/heif/reader.rs:25,59,33; src/heic/decoder.rs:12-112
@@ -223,6 +236,10 @@ const heic_image_desc* heic_b200_file_primary_image(const heic_b200_file* f);
 /* Auxiliary images (e.g. the Apple HDR gain map, `auxl` reference to the primary item). */
 uint32_t heic_b200_file_aux_image_count(const heic_b200_file* f);
 const heic_image_desc* heic_b200_file_aux_image(const heic_b200_file* f, uint32_t i);
+/* The same images with raw tile payloads (heic_tile_desc::escaped = 1): the bytes of the NAL units as they lie in
+ * `mdat`, minus the 2-byte NAL header. */
+const heic_image_desc* heic_b200_file_primary_image_raw(const heic_b200_file* f);
+const heic_image_desc* heic_b200_file_aux_image_raw(const heic_b200_file* f, uint32_t i);
 /* Escaped NAL units (2-byte header included) as stored in the file, e.g. to feed an external decoder.
  * image = -1 selects the primary image, >= 0 an auxiliary image.  nal_unit_type: 32 VPS, 33 SPS, 34 PPS.
  * The pointers stay valid until heic_b200_file_close. */
@@ -312,6 +329,14 @@ typedef struct heic_tile_dump {
 int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_tile_dump* dump);
 
 /* ---- stand-alone stage entry point on caller-owned DEVICE buffers (config 2 of the survey) ---- */
+/* [+] RbspReader::remove_emulation_prevention on the GPU                    src/hevc/rbsp_reader.rs:11-39
+ * One raw NAL payload (after the 2-byte header) in, its RBSP out (rbsp_out holds `len` bytes), plus the slice data
+ * offset and the substream offsets re-based from raw to un-escaped byte counts — the stage heic_b200_decode_grids
+ * runs for heic_tile_desc::escaped tiles, exposed for parity tests against the host function. */
+int32_t heic_b200_unescape(heic_b200_ctx* ctx, const uint8_t* nal_payload, size_t len, uint32_t slice_data_byte_offset,
+                           const uint32_t* substream_offset, uint32_t n_substreams, uint8_t* rbsp_out, size_t* rbsp_len,
+                           uint32_t* slice_data_byte_offset_out, uint32_t* substream_offset_out);
+
 /* YCbCr 4:2:0 -> RGB8 + grid stitch + crop.  planes: n_tiles tiles, each tile_w*tile_h Y followed by
  * Cb and Cr at (tile_w/2)*(tile_h/2), contiguous per tile (tile stride = tile_w*tile_h*3/2).
  * full_range/matrix_coeffs select the integer matrix ("Colour definition"). */

@@ -44,6 +44,8 @@ pub struct heic_tile_desc {
     pub rbsp: *const u8,
     pub rbsp_len: u32,
     pub nal_unit_type: u32,
+    /// 0: `rbsp` is un-escaped; 1: raw NAL payload, offsets in raw byte counts (un-escaped on the GPU)
+    pub escaped: u32,
     pub header: heic_slice_header,
 }
 
@@ -84,6 +86,10 @@ extern "C" {
     pub fn heic_b200_parse_slice_header(
         rbsp: *const u8, len: usize, nal_unit_type: u32, sps: *const heic_sps, pps: *const heic_pps,
         epb_pos: *const u32, n_epb: usize, out: *mut heic_slice_header,
+    ) -> i32;
+    pub fn heic_b200_parse_slice_header_raw(
+        nal_payload: *const u8, len: usize, nal_unit_type: u32, sps: *const heic_sps, pps: *const heic_pps,
+        out: *mut heic_slice_header,
     ) -> i32;
     pub fn heic_b200_decode_grids(
         ctx: *mut heic_b200_ctx, imgs: *const heic_image_desc, n_imgs: u32, rgb_out: *mut u8, pitch: usize,

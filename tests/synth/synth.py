@@ -68,6 +68,20 @@ class Picture:
         d.n_tiles = 1
         d.tiles = C.cast(self._tiles, C.POINTER(K.TileDesc))
         self.desc = d
+        self.n_epb = len(epb)
+        # the same picture as a raw NAL payload: emulation prevention removal and entry-point re-basing happen on the GPU
+        payload = self.slice_nal[2:]
+        self._raw = (K.u8 * len(payload)).from_buffer_copy(payload)
+        self._tiles_raw = (K.TileDesc * 1)()
+        self._tiles_raw[0].rbsp = C.cast(self._raw, C.POINTER(K.u8))
+        self._tiles_raw[0].rbsp_len = len(payload)
+        self._tiles_raw[0].nal_unit_type = 20
+        self._tiles_raw[0].escaped = 1
+        self._tiles_raw[0].header = H.parse_slice_header_raw(payload, 20, self.sps, self.pps)
+        r = K.ImageDesc()
+        C.memmove(C.byref(r), C.byref(d), C.sizeof(K.ImageDesc))
+        r.tiles = C.cast(self._tiles_raw, C.POINTER(K.TileDesc))
+        self.desc_raw = r
 
     @property
     def tile(self):

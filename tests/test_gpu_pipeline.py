@@ -199,3 +199,50 @@ def test_async_submit_wait_two_jobs_in_flight(decoder, heic_file, oracle_rgb):
         hh = min(512, 3024 - r * 512, 3024 - rs * 512)
         ww = min(512, 4032 - c * 512, 4032 - cs * 512)
         assert np.array_equal(out_b[0, r * 512:r * 512 + hh, c * 512:c * 512 + ww], oracle_rgb[rs * 512:rs * 512 + hh, cs * 512:cs * 512 + ww])
+
+
+def test_raw_nal_payloads_unescaped_on_the_gpu(decoder, heic_file, oracle_rgb):
+    """heic_tile_desc::escaped = 1: the library removes the emulation prevention bytes and re-bases the entry points on
+    the GPU (unescape_kernel); alone and mixed with host-unescaped images in one call."""
+    out = decoder.decode_grids([heic_file.primary_raw, heic_file.primary, heic_file.primary_raw])
+    for i in range(3):
+        assert np.array_equal(out[i], oracle_rgb)
+    # a resident batch decoded twice: the re-basing must not be applied a second time
+    b = decoder.batch([heic_file.primary_raw])
+    b.decode()
+    b.decode()
+    b.sync()
+    assert all(s.code == 0 for s in b.status())
+    assert np.array_equal(b.download_rgb()[0], oracle_rgb)
+    b.close()
+
+
+def test_gpu_unescape_matches_reference_vectors_and_host(decoder):
+    """unescape_kernel against the reference's 12 emulation-prevention vectors (rbsp_reader.rs:186-303) and against the
+    host restatement on random payloads dense in 00 00 03 patterns, incl. the re-basing of entry points."""
+    import bisect
+
+    from tests.test_reference_vectors import EPB_CASES
+
+    for data, expected in EPB_CASES:
+        if not data:
+            continue
+        got, _, _ = decoder.unescape(bytes(data))
+        assert list(got) == (data if expected is None else expected), data
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 3, 17, 255, 4096, 4097, 70001):
+        # a small alphabet makes the patterns (and their corner cases: 00 00 03 03, 00 00 00 03, runs of them) frequent
+        payload = rng.choice(np.array([0, 0, 0, 3, 3, 1, 4, 255], np.uint8), size=n).tobytes()
+        rbsp, epb = H.remove_emulation_prevention(payload, with_positions=True)
+        if len(epb) > 1024:
+            continue
+        data_off = min(n, 9)
+        raw_sub = sorted(int(x) for x in rng.integers(0, n - data_off + 1, size=min(16, n)))
+        got, off, sub = decoder.unescape(payload, data_off, raw_sub)
+        assert got == rbsp, n
+        removed = lambda x: bisect.bisect_left(epb, x)
+        assert off == data_off - removed(data_off)
+        assert sub == [data_off + s - removed(data_off + s) - off for s in raw_sub]
+    # more removals in one NAL unit than the kernel's table: rejected, not mis-decoded
+    with pytest.raises(H.HeicError):
+        decoder.unescape(bytes([0, 0, 3]) * 2000)

@@ -63,3 +63,31 @@ def test_heterogeneous_batch_matches_ffmpeg_golden(decoder):
         n_comp = 3 if pic.sps.chroma_format_idc else 1
         got = [hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in planes[:n_comp]]
         assert got == GOLDEN[key]["planes"], key
+
+
+# (seed, config) pairs whose slice data contains an emulation prevention byte — found by search: the arithmetic coder's
+# output is close to random, so 00 00 0x turns up about once per 4 MB
+EPB_SEEDS = (1249, 1914, 3113, 3754, 4324, 5903, 6936, 7057)
+EPB_CONFIG = dict(init_qp_minus26=-20, lps_gain=2.0, width=512, height=256, wpp=1)
+
+
+def test_heterogeneous_batch_from_raw_nal_payloads(decoder):
+    """The same call with every picture shipped as a raw NAL payload (heic_tile_desc::escaped = 1): emulation
+    prevention removal and entry-point re-basing on the GPU, for every geometry of the set plus eight WPP pictures that
+    carry an emulation prevention byte inside their slice data (so the later entry points move)."""
+    pics, keys = [], []
+    for name, cfg in CONFIGS:
+        for seed in SEEDS:
+            pics.append(synth.encode(seed, **cfg))
+            keys.append(f"{name}/{seed}")
+    epb_pics = [synth.encode(seed, **EPB_CONFIG) for seed in EPB_SEEDS]
+    assert all(p.n_epb >= 1 for p in epb_pics)
+    res = decoder.decode_grids_yuv([p.desc_raw for p in pics + epb_pics])
+    for key, pic, planes in zip(keys, pics, res):
+        n_comp = 3 if pic.sps.chroma_format_idc else 1
+        got = [hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in planes[:n_comp]]
+        assert got == GOLDEN[key]["planes"], key
+    for pic, planes in zip(epb_pics, res[len(pics):]):
+        ref = O.decode_picture(pic.sps, pic.pps, pic.header, (pic.tile.rbsp, pic.tile.rbsp_len))
+        for c in range(3):
+            assert np.array_equal(planes[c], ref["plane"][c])

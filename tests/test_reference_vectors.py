@@ -143,3 +143,31 @@ def test_unsupported_and_malformed_inputs_become_error_codes(built):
         H.parse_sps(b"\x01")
     with pytest.raises(H.HeicError):
         H.read_ue(b"\x00\x00\x00\x00\x00")  # no terminating 1 bit
+
+
+def test_raw_slice_header_offsets_rebase_to_the_unescaped_ones(heic_file):
+    """heic_b200_parse_slice_header_raw keeps raw byte counts (7.4.7.1); removing the emulation prevention bytes before
+    each boundary must give the un-escaped offsets the converted header carries (what unescape_kernel does on the GPU)."""
+    import heif_b200 as H
+    import bisect
+
+    img, raw = heic_file.primary, heic_file.primary_raw
+    assert raw.n_tiles == img.n_tiles == 48
+    n_with_epb = 0
+    for t in range(48):
+        a, b = img.tiles[t], raw.tiles[t]
+        assert b.escaped == 1 and a.escaped == 0
+        payload = bytes(b.rbsp[: b.rbsp_len])
+        rbsp, epb = H.remove_emulation_prevention(payload, with_positions=True)
+        assert rbsp == bytes(a.rbsp[: a.rbsp_len])
+        n_with_epb += bool(epb)
+        removed = lambda x: bisect.bisect_left(epb, x)
+        e = b.header.slice_data_byte_offset
+        data_off = e - removed(e)
+        assert data_off == a.header.slice_data_byte_offset
+        n = a.header.num_entry_point_offsets
+        assert b.header.num_entry_point_offsets == n
+        for k in range(n + 1):
+            boundary = e + b.header.substream_offset[k]
+            assert boundary - removed(boundary) - data_off == a.header.substream_offset[k]
+    assert n_with_epb == 2  # SURVEY row H3: exactly two fixture tiles carry an emulation prevention byte
