@@ -185,7 +185,81 @@ struct Engine {
     while (v < cmax && bypass()) v++;
     return v;
   }
+  HEIC_HD uint32_t egk_bypass(int k, int& bad) {  // decoder.rs:206-222 with 32-bit arithmetic
+    int ones = 0;
+    while (bypass()) {
+      if (++ones > 31) {
+        bad = 1;
+        return 0;
+      }
+    }
+    uint32_t suffix = fl_bypass(ones + k);
+    return (((1u << ones) - 1u) << k) + suffix;
+  }
+  HEIC_HD uint32_t coeff_abs_level_remaining(int rice, int& bad) {  // decoder.rs:224-261
+    uint32_t prefix = 0;
+    while (prefix < 4 && bypass()) prefix++;
+    if (prefix < 4) return (prefix << rice) + fl_bypass(rice);
+    return (4u << rice) + egk_bypass(rice + 1, bad);
+  }
 };
+
+#if defined(__CUDA_ARCH__) && !defined(HEIC_CABAC_INLINE_ENGINE)
+// Out-of-line engine entry points for the device parser.  The engine lives in registers and travels by value (the
+// compiler passes and returns the struct in registers), so a call costs a CALL/RET pair; in exchange the decoding
+// routines exist once instead of at ~45 call sites.  Inlined everywhere the kernel was 7 K instructions (113 KB) against
+// a 32 KB instruction cache and `stall_no_instruction` was its largest stall reason.
+#define HEIC_CABAC_OUTLINED 1
+struct EngRet {
+  Engine e;
+  uint32_t v;
+  int bad;
+};
+static __device__ __noinline__ EngRet eng_decision(Engine e, uint32_t ctx_addr) {
+  uint32_t s = heic_cabac_smem[ctx_addr];
+  EngRet r;
+  r.v = (uint32_t)e.decision(reinterpret_cast<const CabacTabs*>(heic_cabac_smem), s);
+  heic_cabac_smem[ctx_addr] = (uint8_t)s;
+  r.e = e;
+  r.bad = 0;
+  return r;
+}
+static __device__ __noinline__ EngRet eng_bypass(Engine e) {
+  EngRet r;
+  r.v = (uint32_t)e.bypass();
+  r.e = e;
+  r.bad = 0;
+  return r;
+}
+static __device__ __noinline__ EngRet eng_fl_bypass(Engine e, int n) {
+  EngRet r;
+  r.v = e.fl_bypass(n);
+  r.e = e;
+  r.bad = 0;
+  return r;
+}
+static __device__ __noinline__ EngRet eng_tr_bypass(Engine e, uint32_t cmax) {
+  EngRet r;
+  r.v = e.tr_bypass(cmax);
+  r.e = e;
+  r.bad = 0;
+  return r;
+}
+static __device__ __noinline__ EngRet eng_egk_bypass(Engine e, int k) {
+  EngRet r;
+  r.bad = 0;
+  r.v = e.egk_bypass(k, r.bad);
+  r.e = e;
+  return r;
+}
+static __device__ __noinline__ EngRet eng_calr(Engine e, int rice) {
+  EngRet r;
+  r.bad = 0;
+  r.v = e.coeff_abs_level_remaining(rice, r.bad);
+  r.e = e;
+  return r;
+}
+#endif
 
 // 9.3.2.2 (arithmetic.rs:40-78): initValue -> pStateIdx << 1 | valMps
 HEIC_HD uint8_t context_init_state(int init_value, int slice_qp) {
@@ -232,10 +306,16 @@ struct Parser {
   HEIC_HD void st_ctx(int idx, uint32_t v) { ctx[idx * STRIDE] = (uint8_t)v; }
 #endif
   HEIC_HD int dec(int idx) {
+#if defined(HEIC_CABAC_OUTLINED)
+    const EngRet r = eng_decision(e, ctx_off + idx * STRIDE);
+    e = r.e;
+    return (int)r.v;
+#else
     uint32_t s = ld_ctx(idx);
     const int bin = e.decision(tabs(), s);
     st_ctx(idx, s);
     return bin;
+#endif
   }
   HEIC_HD void fail(int code) {
     if (!err) err = code;
@@ -245,6 +325,39 @@ struct Parser {
     for (int i = 0; i < NUM_CTX; i++) st_ctx(i, context_init_state(tabs()->init_value[i], slice_qp));
   }
 
+  // bypass-coded elements
+#if defined(HEIC_CABAC_OUTLINED)
+  HEIC_HD int byp() {
+    const EngRet r = eng_bypass(e);
+    e = r.e;
+    return (int)r.v;
+  }
+  HEIC_HD uint32_t fl_bypass(int n) {
+    const EngRet r = eng_fl_bypass(e, n);
+    e = r.e;
+    return r.v;
+  }
+  HEIC_HD uint32_t tr_bypass(uint32_t cmax) {
+    const EngRet r = eng_tr_bypass(e, cmax);
+    e = r.e;
+    return r.v;
+  }
+  HEIC_HD uint32_t egk_bypass(int k) {
+    const EngRet r = eng_egk_bypass(e, k);
+    e = r.e;
+    if (r.bad) fail(-3);
+    return r.v;
+  }
+  HEIC_HD uint32_t coeff_abs_level_remaining(int rice) {
+    const EngRet r = eng_calr(e, rice);
+    e = r.e;
+    if (r.bad) fail(-3);
+    return r.v;
+  }
+#else
+  HEIC_HD int byp() { return e.bypass(); }
+  HEIC_HD uint32_t fl_bypass(int n) { return e.fl_bypass(n); }
+  HEIC_HD uint32_t tr_bypass(uint32_t cmax) { return e.tr_bypass(cmax); }
   HEIC_HD uint32_t egk_bypass(int k) {  // decoder.rs:206-222 with 32-bit arithmetic
     int ones = 0;
     while (e.bypass()) {
@@ -262,6 +375,7 @@ struct Parser {
     if (prefix < 4) return (prefix << rice) + e.fl_bypass(rice);
     return (4u << rice) + egk_bypass(rice + 1);
   }
+#endif
 
   // ---- 7.3.8.3 sao() (todo!() at slice.rs:249-251) -------------------------------------------
   HEIC_HD void parse_sao(int rx, int ry) {
@@ -287,25 +401,25 @@ struct Parser {
         type = type_c;
       } else {  // sao_type_idx: TR cMax 2, bin 0 context coded, bin 1 bypass (decoder.rs:93-100)
         type = 0;
-        if (dec(CTX_SAO_TYPE)) type = e.bypass() ? 2 : 1;
+        if (dec(CTX_SAO_TYPE)) type = byp() ? 2 : 1;
         if (c == 1) type_c = type;
       }
       if (!type) continue;
       uint32_t abs4 = 0;  // four sao_offset_abs, 4 bits each
-      for (int i = 0; i < 4; i++) abs4 |= e.tr_bypass(7) << (4 * i);
+      for (int i = 0; i < 4; i++) abs4 |= tr_bypass(7) << (4 * i);
       uint32_t v = (uint32_t)type;
       if (type == 1) {
         for (int i = 0; i < 4; i++) {
           const int a = (int)((abs4 >> (4 * i)) & 15u);
-          const int neg = a ? e.bypass() : 0;
+          const int neg = a ? byp() : 0;
           const int o = neg ? -a : a;
           v |= ((uint32_t)o & 15u) << (8 + 4 * i);
         }
-        v |= e.fl_bypass(5) << 2;  // sao_band_position
+        v |= fl_bypass(5) << 2;  // sao_band_position
       } else {
         int cl;
-        if (c == 0) cl = (int)e.fl_bypass(2);
-        else if (c == 1) cl = class_c = (int)e.fl_bypass(2);
+        if (c == 0) cl = (int)fl_bypass(2);
+        else if (c == 1) cl = class_c = (int)fl_bypass(2);
         else cl = class_c;
         v |= (uint32_t)cl << 2;
         v |= (abs4 & 15u) << 8;
@@ -382,7 +496,7 @@ HEIC_NO_UNROLL
         const int pv = (int)((pre >> (8 * d)) & 0xffu);
         if (pv > 3) {
           const int nb = (pv >> 1) - 1;
-          const int full = (1 << nb) * (2 + (pv & 1)) + (int)e.fl_bypass(nb);
+          const int full = (1 << nb) * (2 + (pv & 1)) + (int)fl_bypass(nb);
           pre = (pre & ~(0xffu << (8 * d))) | ((uint32_t)full << (8 * d));
         }
       }
@@ -478,7 +592,7 @@ HEIC_NO_UNROLL
         while (m) {
           int k = 31 - HEIC_CLZ(m);
           m &= ~(1u << k);
-          if (e.bypass()) sign |= 1u << k;
+          if (byp()) sign |= 1u << k;
         }
       }
       int num_sig = 0, sum_abs = 0, rice = 0;
@@ -539,7 +653,7 @@ HEIC_NO_UNROLL
       int v = 0;
       while (v < 5 && dec(CTX_CU_QP_DELTA + (v ? 1 : 0))) v++;
       if (v == 5) v += (int)egk_bypass(0);
-      int neg = v ? e.bypass() : 0;
+      int neg = v ? byp() : 0;
       is_cu_qp_delta_coded = 1;
       cu_qp_delta_val = neg ? -v : v;
       if (cu_qp_delta_val < -26 || cu_qp_delta_val > 25) fail(-3);
@@ -676,8 +790,8 @@ HEIC_NO_UNROLL
     for (int k = 0; k < n_pu; k++) {
       int mpm_idx = 0, rem = 0;
       const int prev_k = (int)((prev >> k) & 1u);
-      if (prev_k) mpm_idx = (int)e.tr_bypass(2);
-      else rem = (int)e.fl_bypass(5);
+      if (prev_k) mpm_idx = (int)tr_bypass(2);
+      else rem = (int)fl_bypass(5);
       int px = x0 + (k & 1) * pb, py = y0 + (k >> 1) * pb;
       int mode = derive_luma_mode(px, py, prev_k, mpm_idx, rem);
       pu_modes |= (uint32_t)mode << (8 * k);
@@ -690,7 +804,7 @@ HEIC_NO_UNROLL
     chroma_mode = 0;
     if (pp->chroma) {  // intra_chroma_pred_mode (decoder.rs:23-35,192-204) + 8.4.3
       int idx = 4;
-      if (dec(CTX_CHROMA_PRED)) idx = (int)e.fl_bypass(2);
+      if (dec(CTX_CHROMA_PRED)) idx = (int)fl_bypass(2);
       const int luma = (int)(pu_modes & 0xffu);
       if (idx == 4) {
         chroma_mode = luma;
