@@ -177,16 +177,19 @@ struct Engine {
   }
   HEIC_HD uint32_t fl_bypass(int n) {  // decoder.rs:152-164
     uint32_t v = 0;
+    HEIC_NO_UNROLL
     for (int i = 0; i < n; i++) v = (v << 1) | (uint32_t)bypass();
     return v;
   }
   HEIC_HD uint32_t tr_bypass(uint32_t cmax) {  // decoder.rs:166-190, cRiceParam 0
     uint32_t v = 0;
+    HEIC_NO_UNROLL
     while (v < cmax && bypass()) v++;
     return v;
   }
   HEIC_HD uint32_t egk_bypass(int k, int& bad) {  // decoder.rs:206-222 with 32-bit arithmetic
     int ones = 0;
+    HEIC_NO_UNROLL
     while (bypass()) {
       if (++ones > 31) {
         bad = 1;
@@ -198,6 +201,7 @@ struct Engine {
   }
   HEIC_HD uint32_t coeff_abs_level_remaining(int rice, int& bad) {  // decoder.rs:224-261
     uint32_t prefix = 0;
+    HEIC_NO_UNROLL
     while (prefix < 4 && bypass()) prefix++;
     if (prefix < 4) return (prefix << rice) + fl_bypass(rice);
     return (4u << rice) + egk_bypass(rice + 1, bad);
