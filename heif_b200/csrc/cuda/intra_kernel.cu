@@ -89,6 +89,55 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
     lo = left_ok ? N - n_bl : 2 * N + 1;
     hi = top_ok ? 3 * N + n_tr : 2 * N - 1;  // lo > hi: nothing available -> 1 << (bitDepth - 1)
   }
+  if (log2 == 2 && !pair) {
+    // ---- luma 4x4 (half of all calls): the 17 reference samples live in lanes 0..16 (lane s holds scan position s, so
+    // left(i) is lane 8 - i and top(i) lane 8 + i), the 16 samples in lanes 0..15, and shuffles replace the reference
+    // arrays, their loops and two warp barriers.  No smoothing at this size.
+    const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
+    int r = 128;
+    if (lane <= 16 && lo <= hi) {
+      const int d = min(max(lane, lo), hi) - 8;
+      r = corner[d <= 0 ? -d * stride : d];
+    }
+    const int x = lane & 3, y = (lane >> 2) & 3;
+    const int L = __shfl_sync(0xffffffffu, r, 7 - y), T = __shfl_sync(0xffffffffu, r, 9 + x);  // left(1 + y), top(1 + x)
+    int v;
+    if (mode == 0) {
+      const int tr = __shfl_sync(0xffffffffu, r, 13), bl = __shfl_sync(0xffffffffu, r, 3);
+      v = ((3 - x) * L + (x + 1) * tr + (3 - y) * T + (y + 1) * bl + 4) >> 3;
+    } else if (mode == 1) {
+      const bool in_sum = (lane >= 4 && lane <= 7) || (lane >= 9 && lane <= 12);
+      const int dc = ((int)__reduce_add_sync(0xffffffffu, in_sum ? (unsigned)r : 0u) + 4) >> 3;
+      v = dc;
+      if (y == 0) v = x == 0 ? (L + 2 * dc + T + 2) >> 2 : (T + 3 * dc + 2) >> 2;
+      else if (x == 0) v = (L + 3 * dc + 2) >> 2;
+    } else {
+      const int angle = kIntraPredAngle[mode];
+      const bool vertical = mode >= 18;
+      const int dir = vertical ? 1 : -1;
+      const int t = ((vertical ? y : x) + 1) * angle, fact = t & 31;
+      const int t1 = (vertical ? x : y) + (t >> 5) + 1;
+      int la = 8 + dir * t1, lb = la + dir;
+      if (angle < 0) {  // negative positions of the angular array are projections of the other edge
+        const int inv = kInvAngle[mode - 11];
+        if (t1 < 0) la = 8 - dir * ((t1 * inv + 128) >> 8);
+        if (t1 + 1 < 0) lb = 8 - dir * (((t1 + 1) * inv + 128) >> 8);
+      }
+      const int a = __shfl_sync(0xffffffffu, r, la), b = __shfl_sync(0xffffffffu, r, lb);  // b unused when fact == 0
+      v = ((32 - fact) * a + fact * b + 16) >> 5;
+      if (mode == 26 || mode == 10) {
+        const int c0 = __shfl_sync(0xffffffffu, r, 8), t1s = __shfl_sync(0xffffffffu, r, 9), l1s = __shfl_sync(0xffffffffu, r, 7);
+        if (mode == 26 && x == 0) v = clip8(t1s + ((L - c0) >> 1));
+        if (mode == 10 && y == 0) v = clip8(l1s + ((T - c0) >> 1));
+      }
+    }
+    if (lane < 16) {
+      if (cbf_a) v = clip8(v + (int)resid[lane]);
+      buf[(by + 1 + y) * stride + bx + 16 + x] = (uint8_t)v;
+    }
+    __syncwarp();
+    return;
+  }
   {
     const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
     const int n_ref = pair ? 2 * cnt : cnt;
