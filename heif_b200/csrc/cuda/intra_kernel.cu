@@ -330,7 +330,9 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
   const int n_planes = pp->chroma ? 3 : 1;
   const int n4sq = c.ctb4 * c.ctb4;
   {
-    unsigned char* p = smem_raw + progress_bytes + (size_t)slot * L.warp_bytes;
+    uint32_t wbase = (uint32_t)progress_bytes + (uint32_t)slot * (uint32_t)L.warp_bytes;
+    asm volatile("" : "+r"(wbase));  // opaque: keeps the warp's base offset in a register instead of re-deriving it per use
+    unsigned char* p = smem_raw + wbase;
     c.res[0] = reinterpret_cast<int16_t*>(p);
     c.res[1] = reinterpret_cast<int16_t*>(p + L.res1);
     c.res[2] = reinterpret_cast<int16_t*>(p + L.res2);
@@ -389,10 +391,12 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
           for (int y = lane; y < cs; y += 32) b[(y + 1) * st + 15] = b[(y + 1) * st + 16 + cs - 1];
         if (ry > 0) {
           const int wp = c.w >> sub, x0 = (c.x_ctb >> sub) - 1, y0 = (c.y_ctb >> sub) - 1;
+          // aligned 4-byte words from x_ctb - 4 (its last byte is the corner sample) to the end of the above-right CTU;
+          // plane widths are multiples of 4, so a word is inside the picture or outside it as a whole
           const uint8_t* src = plane[pl] + (size_t)y0 * pitch[pl];
-          for (int i = lane; i <= 2 * cs; i += 32) {
-            const int x = x0 + i;
-            if (x >= 0 && x < wp) b[15 + i] = __ldcg(src + x);
+          for (int j = lane; j <= cs / 2; j += 32) {
+            const int x = x0 - 3 + 4 * j;
+            if (x >= 0 && x < wp) *reinterpret_cast<uint32_t*>(b + 12 + 4 * j) = __ldcg(reinterpret_cast<const uint32_t*>(src + x));
           }
         }
       }
