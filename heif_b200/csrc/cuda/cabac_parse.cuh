@@ -48,8 +48,10 @@ struct CabacTabs {
 #endif
 #if defined(__CUDA_ARCH__)
 #define HEIC_CLZ(x) __clz(x)
+#define HEIC_POPC(x) __popc(x)
 #else
 #define HEIC_CLZ(x) ((x) ? __builtin_clz(x) : 32)
+#define HEIC_POPC(x) __builtin_popcount(x)
 #endif
 
 HEIC_HD int clip3i(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -589,16 +591,10 @@ HEIC_NO_UNROLL
       const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
       int g2 = 0;
       if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
-      uint32_t sign = 0;
-      {
-        uint32_t m = sig;
-        if (sign_hidden) m &= ~(1u << first_sig);
-        while (m) {
-          int k = 31 - HEIC_CLZ(m);
-          m &= ~(1u << k);
-          if (byp()) sign |= 1u << k;
-        }
-      }
+      // coeff_sign_flag: one bypass bin per coefficient in scan order (none for the hidden one, which comes last):
+      // read them in one go, most significant bit = first coefficient
+      const int n_sign = HEIC_POPC(sig) - (sign_hidden ? 1 : 0);
+      uint32_t sign_bits = n_sign ? fl_bypass(n_sign) << (32 - n_sign) : 0u;
       int num_sig = 0, sum_abs = 0, rice = 0;
       uint32_t m = sig;
       while (m) {
@@ -615,7 +611,8 @@ HEIC_NO_UNROLL
           abs_level = base + (int)rem;
           if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
         }
-        int v = ((sign >> k) & 1u) ? -abs_level : abs_level;
+        int v = (sign_bits >> 31) ? -abs_level : abs_level;
+        sign_bits <<= 1;
         if (sign_hidden) {
           sum_abs += abs_level;
           if (k == first_sig && (sum_abs & 1)) v = -v;
