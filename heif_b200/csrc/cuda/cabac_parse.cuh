@@ -230,6 +230,24 @@ static __device__ __noinline__ EngRet eng_decision(Engine e, uint32_t ctx_addr) 
   r.bad = 0;
   return r;
 }
+// sig_coeff_flag of scan positions n_start .. 1 of one sub-block (9.3.4.2.5): context of position k = nibble k of `nib`,
+// entries `1 << stride_shift` bytes apart from ctx_addr.  One call per sub-block instead of one per bin.
+static __device__ __noinline__ EngRet eng_sig_run(Engine e, uint32_t ctx_addr, uint64_t nib, int n_start, int stride_shift) {
+  const CabacTabs* T = reinterpret_cast<const CabacTabs*>(heic_cabac_smem);
+  uint32_t sig = 0;
+  HEIC_NO_UNROLL
+  for (int k = n_start; k > 0; k--) {
+    const uint32_t a = ctx_addr + ((uint32_t)((nib >> (4 * k)) & 15u) << stride_shift);
+    uint32_t s = heic_cabac_smem[a];
+    if (e.decision(T, s)) sig |= 1u << k;
+    heic_cabac_smem[a] = (uint8_t)s;
+  }
+  EngRet r;
+  r.e = e;
+  r.v = sig;
+  r.bad = 0;
+  return r;
+}
 static __device__ __noinline__ EngRet eng_bypass(Engine e) {
   EngRet r;
   r.v = (uint32_t)e.bypass();
@@ -333,6 +351,11 @@ struct Parser {
 
   // bypass-coded elements
 #if defined(HEIC_CABAC_OUTLINED)
+  HEIC_HD uint32_t sig_run(int add, uint64_t nib, int n_start) {
+    const EngRet r = eng_sig_run(e, ctx_off + add * STRIDE, nib, n_start, STRIDE == 32 ? 5 : 0);
+    e = r.e;
+    return r.v;
+  }
   HEIC_HD int byp() {
     const EngRet r = eng_bypass(e);
     e = r.e;
@@ -361,6 +384,12 @@ struct Parser {
     return r.v;
   }
 #else
+  HEIC_HD uint32_t sig_run(int add, uint64_t nib, int n_start) {
+    uint32_t sig = 0;
+    for (int k = n_start; k > 0; k--)
+      if (dec(add + (int)((nib >> (4 * k)) & 15u))) sig |= 1u << k;
+    return sig;
+  }
   HEIC_HD int byp() { return e.bypass(); }
   HEIC_HD uint32_t fl_bypass(int n) { return e.fl_bypass(n); }
   HEIC_HD uint32_t tr_bypass(uint32_t cmax) { return e.tr_bypass(cmax); }
@@ -550,8 +579,7 @@ HEIC_NO_UNROLL
         // sigCtx (9.3.4.2.5) of all 16 scan positions of this sub-block as one word of nibbles + one additive term
         const uint64_t nib = tabs()->sig_nib[log2 == 2 ? scan_idx : 3 + scan_idx * 4 + prev_csbf];
         const int add = sig_base + (log2 == 2 ? 0 : ((c_idx == 0 && (xs | ys)) ? 3 : 0) + sig_off);
-        for (int k = n_start; k > 0; k--)
-          if (dec(add + (int)((nib >> (4 * k)) & 15u))) sig |= 1u << k;
+        if (n_start > 0) sig |= sig_run(add, nib, n_start);
         if (n_start >= 0) {
           if (infer_sb_dc && sig == 0) {
             sig = 1u;  // inferred DC of a coded sub-block with no other significant coefficient
