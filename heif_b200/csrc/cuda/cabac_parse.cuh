@@ -248,6 +248,35 @@ static __device__ __noinline__ EngRet eng_sig_run(Engine e, uint32_t ctx_addr, u
   r.bad = 0;
   return r;
 }
+// coeff_abs_level_greater1_flag of up to eight coefficients of a sub-block (9.3.4.2.6): ctx_addr is context 0 of the
+// sub-block's context set; returns the flags as a mask, greater1Ctx and the first position with the flag set in `bad`.
+static __device__ __noinline__ EngRet eng_gt1_run(Engine e, uint32_t ctx_addr, uint32_t sig, int stride_shift) {
+  const CabacTabs* T = reinterpret_cast<const CabacTabs*>(heic_cabac_smem);
+  uint32_t g1 = 0, m = sig;
+  int greater1_ctx = 1, num = 0, last = -1;
+  HEIC_NO_UNROLL
+  while (m && num < 8) {
+    const int k = 31 - __clz(m);
+    m &= ~(1u << k);
+    const uint32_t a = ctx_addr + ((uint32_t)greater1_ctx << stride_shift);
+    uint32_t s = heic_cabac_smem[a];
+    const int f = e.decision(T, s);
+    heic_cabac_smem[a] = (uint8_t)s;
+    num++;
+    if (f) {
+      g1 |= 1u << k;
+      greater1_ctx = 0;
+      if (last < 0) last = k;
+    } else if (greater1_ctx > 0 && greater1_ctx < 3) {
+      greater1_ctx++;
+    }
+  }
+  EngRet r;
+  r.e = e;
+  r.v = g1;
+  r.bad = greater1_ctx | ((last + 1) << 8);
+  return r;
+}
 static __device__ __noinline__ EngRet eng_bypass(Engine e) {
   EngRet r;
   r.v = (uint32_t)e.bypass();
@@ -597,11 +626,21 @@ HEIC_NO_UNROLL
       first_sub_block = 0;
       greater1_ctx = 1;
       uint32_t g1 = 0;
-      int num_g1 = 0, last_g1_pos = -1;
+      int last_g1_pos = -1;
       const int last_sig = 31 - HEIC_CLZ(sig);
       const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
+#if defined(HEIC_CABAC_OUTLINED)
+      {
+        const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0);
+        e = r.e;
+        g1 = r.v;
+        greater1_ctx = r.bad & 0xff;
+        last_g1_pos = (r.bad >> 8) - 1;
+      }
+#else
       {
         uint32_t m = sig;
+        int num_g1 = 0;
         while (m && num_g1 < 8) {
           int k = 31 - HEIC_CLZ(m);
           m &= ~(1u << k);
@@ -616,6 +655,7 @@ HEIC_NO_UNROLL
           }
         }
       }
+#endif
       const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
       int g2 = 0;
       if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
