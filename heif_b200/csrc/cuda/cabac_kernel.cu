@@ -32,8 +32,10 @@ constexpr int kMaxRows = 512;
 
 struct CtaShared {
   CabacTabs tabs;
-  int progress[kMaxRows];  // CTUs finished per CTB row (TILES == 32: by all lanes of the row's warp)
-  int aborted[32];         // per tile of the CTA
+  int progress[kMaxRows];  // CTUs finished per CTB row (TILES == 32: by all lanes of the row's warp), plus the
+                           // group's base (see cabac_kernel): values only ever grow
+  int aborted[32];         // per tile of the CTA: use + 1 of the group in which the tile failed
+  unsigned group_slot[4];  // persistent CTAs: group taken for use k in slot k & 3, tagged with the use
 };
 
 template <int TILES>
@@ -45,39 +47,41 @@ struct SmemSync {
   uint8_t* save_base;     // this tile's WPP context snapshots in HBM, NUM_CTX_PAD bytes per CTB row (written once and
                           // read once per row, so they need not occupy shared memory: that is what bounds occupancy)
   int lane;
+  int base;               // added to every progress value of the current group (persistent CTAs)
+  int use1;               // current use + 1
 
   __device__ __forceinline__ bool wait(int row, int n) {
     unsigned ns = 32;
     if (TILES == 1) {
-      while (progress[row] < n && !*aborted) {
+      while (progress[row] < base + n && *aborted != use1) {
         __nanosleep(ns);
         if (ns < 2048) ns *= 2;
       }
     } else {
       __syncwarp();
       if (lane == 0)
-        while (progress[row] < n) {
+        while (progress[row] < base + n) {
           __nanosleep(ns);
           if (ns < 2048) ns *= 2;
         }
       __syncwarp();
     }
     __threadfence_block();
-    return !*aborted;
+    return *aborted != use1;
   }
   __device__ __forceinline__ void publish(int row, int n) {
     __threadfence_block();
     if (TILES == 1) {
-      progress[row] = n;
+      progress[row] = base + n;
     } else {
       __syncwarp();
-      if (lane == 0) progress[row] = n;
+      if (lane == 0) progress[row] = base + n;
     }
   }
   __device__ __forceinline__ uint8_t* save_area(int row) { return save_base + (size_t)row * NUM_CTX_PAD; }
   __device__ __forceinline__ void abort(int code) {
     if (code != -100) atomicCAS(status_code, 0, code);
-    *aborted = 1;
+    *aborted = use1;
     __threadfence_block();
   }
 };
@@ -86,7 +90,8 @@ struct SmemSync {
 
 template <int TILES>
 __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CABAC_MIN_CTAS : 1) cabac_kernel(Arenas A, const CabacTabs* __restrict__ gtabs,
-                                                    const uint32_t* __restrict__ order, int n_slots) {
+                                                    const uint32_t* __restrict__ order, int n_slots, uint32_t n_groups,
+                                                    uint32_t* group_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
   uint8_t* ctx_all = smem_raw + ((sizeof(CtaShared) + 15) & ~(size_t)15);
@@ -97,15 +102,48 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
     for (int i = threadIdx.x; i < (int)(sizeof(CabacTabs) / 4); i += blockDim.x) dst[i] = src[i];
     for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) sh->progress[i] = 0;
     if (threadIdx.x < 32) sh->aborted[threadIdx.x] = 0;
+    if (threadIdx.x < 4) sh->group_slot[threadIdx.x] = 0;
   }
   __syncthreads();
 
   const int slot = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (TILES == 1 && lane != 0) return;
+  // Persistent CTAs (group_counter != nullptr): a CTA takes group after group from a global counter, and its warps
+  // move on to the next group one by one, without a CTA-wide barrier — warp 0 starts the first CTB rows of the next
+  // group while the last warps still finish the last rows of the current one, so the ramp-up and drain of the WPP
+  // wavefront (14 of a 512x512 tile's 46 steps) overlap.  The first warp to need use k claims the group for it.
+  for (int use = 0;; use++) {
+  uint32_t group = blockIdx.x;
+  if (group_counter) {
+    uint32_t g = 0;
+    if (lane == 0) {
+      volatile unsigned* gs = &sh->group_slot[use & 3];
+      const unsigned tag = ((unsigned)(use + 1) & 0x7ffu) << 20;
+      for (;;) {
+        const unsigned e = *gs;
+        if ((e & 0x7ff00000u) == tag) {
+          if ((e & 0xfffffu) != 0xfffffu) {  // taken and filled in
+            g = e & 0xfffffu;
+            break;
+          }
+          __nanosleep(64);
+        } else if (atomicCAS(const_cast<unsigned*>(gs), e, tag | 0xfffffu) == e) {
+          g = min(atomicAdd(group_counter, 1u), 0xffffeu);
+          *gs = tag | g;
+          __threadfence_block();
+          break;
+        }
+      }
+    }
+    group = __shfl_sync(0xffffffffu, g, 0);
+    if (group >= n_groups) break;
+  } else if (use > 0) {
+    break;
+  }
   // Idle lanes of a partially filled CTA shadow the geometry of the CTA's first tile but decode nothing.
-  const uint32_t my = order[blockIdx.x * TILES + (TILES == 1 ? 0 : lane)];
+  const uint32_t my = order[group * TILES + (TILES == 1 ? 0 : lane)];
   const bool active = my != 0xffffffffu;
-  const uint32_t tile = active ? my : order[blockIdx.x * TILES];
+  const uint32_t tile = active ? my : order[group * TILES];
   const TileParams* tp = A.tiles + tile;
   const PicParams* pp = A.pics + tp->pic;
 
@@ -133,14 +171,17 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   sync.aborted = &sh->aborted[TILES == 1 ? 0 : lane];
   sync.status_code = &A.status[tile].code;
   sync.lane = lane;
+  sync.base = use << 12;
+  sync.use1 = use + 1;
   sync.save_base = A.wpp_save + tp->wpp_off;
-  if (!active) *sync.aborted = 1;
+  if (!active) *sync.aborted = use + 1;
 
   const uint32_t ctus = parse_rows<TILES>(P, A.substreams + tp->sub_first, slot, n_slots, sync);
   if (active) {
     atomicAdd(&A.status[tile].bins, P.e.bins);
     atomicAdd(&A.status[tile].ctus, ctus);
   }
+  }  // next group
 }
 
 size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
@@ -148,7 +189,7 @@ size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
 }
 
 cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,
-                         int tiles_per_cta, int n_slots, cudaStream_t stream) {
+                         int tiles_per_cta, int n_slots, uint32_t* group_counter, int n_sm, int resident_ctas, cudaStream_t stream) {
   if (!n_groups) return cudaSuccess;
   // Experiment knob: extra (unused) dynamic shared memory per CTA caps the CTAs per SM, leaving registers for
   // kernels of another stream to co-reside with this latency-bound one.
@@ -162,9 +203,14 @@ cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t*
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    cabac_kernel<32><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots);
+    // persistent CTAs when there is more than one wave of groups (group ids are 20 bits in the hand-over slot)
+    const uint32_t resident = resident_ctas > 0 ? (uint32_t)resident_ctas : (uint32_t)n_sm * HEIC_CABAC_MIN_CTAS;
+    if (group_counter && n_groups > resident && n_groups < 0xffff0u)
+      cabac_kernel<32><<<resident, threads, smem, stream>>>(A, tabs, order, n_slots, n_groups, group_counter);
+    else
+      cabac_kernel<32><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots, n_groups, nullptr);
   } else {
-    cabac_kernel<1><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots);
+    cabac_kernel<1><<<n_groups, threads, smem, stream>>>(A, tabs, order, n_slots, n_groups, nullptr);
   }
   return cudaGetLastError();
 }

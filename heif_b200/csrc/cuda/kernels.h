@@ -13,8 +13,11 @@ struct CabacTabs;
 // order: n_groups * tiles_per_cta tile indices (0xffffffff = idle lane); all tiles of one group share
 // their PicParams geometry.  n_slots = row slots (warps) per CTA.
 size_t cabac_smem_bytes(int tiles_per_cta, int n_slots);
+// group_counter: a zeroed device word; when given (and there is more than one wave of groups) the thread-per-substream
+// mapping runs as persistent CTAs that take their groups from it
 cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,
-                         int tiles_per_cta, int n_slots, cudaStream_t stream);
+                         int tiles_per_cta, int n_slots, uint32_t* group_counter, int n_sm, int resident_ctas /* 0: fill the GPU */,
+                         cudaStream_t stream);
 
 // Stage 2 — scaling (8.6.4.2) + inverse DST/DCT (8.6.4.2), in place on the coefficient arena.
 // Emulation-prevention removal (7.4.2 / rbsp_reader.rs:11-39) and entry-point re-basing for the tiles shipped raw:

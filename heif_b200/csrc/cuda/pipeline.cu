@@ -111,6 +111,8 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
+  int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
+  int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
   int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
   // decode_grids pipeline: chunks of `pipe_chunk` images rotate over up to kPipe slots, each with its own stream and
   // scratch batch, so the H2D copy, the kernels and the D2H copy of different chunks overlap
@@ -158,7 +160,7 @@ struct heic_b200_batch {
   PinnedBuf h_bitstream, h_status, h_params;
   size_t off_sub = 0, off_order = 0, off_heavy = 0, off_pics = 0, off_tiles = 0, off_scaling = 0;  // inside the parameter blob
   DevBuf d_bitstream, d_params, d_tu, d_coeff, d_recon, d_final, d_ipm, d_ctd,
-      d_qp, d_sao, d_wpp, d_status, d_rgb, d_list, d_list_count, d_raw;
+      d_qp, d_sao, d_wpp, d_status, d_rgb, d_list, d_list_count, d_raw, d_counters;
   PinnedBuf h_raw;
   uint32_t list_off[LIST_CLASSES] = {};
   Arenas arenas() const {
@@ -446,10 +448,16 @@ void heic_b200_batch::run(uint32_t mask) {
       CU(launch_unescape(A, (TileParams*)(pb + off_tiles), (uint32_t*)(pb + off_sub), st));
       ctx->launches++;
     }
+    constexpr size_t kCounters = 64;  // one group counter per launch class (persistent CABAC CTAs)
+    d_counters.ensure(kCounters * sizeof(uint32_t));
+    const bool persistent = ctx->cabac_persistent && classes.size() <= kCounters;
+    if (persistent) CU(cudaMemsetAsync(d_counters.p, 0, kCounters * sizeof(uint32_t), st));
+    size_t ci = 0;
     for (const CabacClass& c : classes) {
       CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, tiles_per_cta,
-                      c.n_slots, st));
+                      c.n_slots, persistent ? (uint32_t*)d_counters.p + ci : nullptr, ctx->n_sm, ctx->cabac_resident, st));
       ctx->launches++;
+      ci++;
     }
   }
   if (mask & HEIC_STAGE_TRANSFORM) {
@@ -575,6 +583,8 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->pipe_chunk = std::max(1, env_int("HEIC_B200_PIPE_CHUNK", 32));
     c->low_latency_tiles = env_int("HEIC_B200_LOW_LATENCY_TILES", 384);
     c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
+    c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
+    c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;

@@ -61,15 +61,20 @@ def decoder(built, request):
     the 32-tiles-per-CTA thread-per-substream kernel that large batches (bench.py) run."""
     import heif_b200
 
-    old = os.environ.get("HEIC_B200_LOW_LATENCY_TILES")
+    knobs = {}
     if request.param == "thread_per_substream":
-        os.environ["HEIC_B200_LOW_LATENCY_TILES"] = "0"
+        # ... and with two persistent CTAs, so that every load of more than 64 tiles exercises the warp-by-warp
+        # hand-over from one group of tiles to the next
+        knobs = {"HEIC_B200_LOW_LATENCY_TILES": "0", "HEIC_B200_CABAC_RESIDENT": "2"}
+    old = {k: os.environ.get(k) for k in knobs}
+    os.environ.update(knobs)
     try:
         dec = heif_b200.HeicDecoder(device=0)
     finally:
-        if old is None:
-            os.environ.pop("HEIC_B200_LOW_LATENCY_TILES", None)
-        else:
-            os.environ["HEIC_B200_LOW_LATENCY_TILES"] = old
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
     yield dec
     dec.close()
