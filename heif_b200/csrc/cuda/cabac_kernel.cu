@@ -204,7 +204,8 @@ cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t*
       attr_set = true;
     }
     // persistent CTAs when there is more than one wave of groups (group ids are 20 bits in the hand-over slot)
-    const uint32_t resident = resident_ctas > 0 ? (uint32_t)resident_ctas : (uint32_t)n_sm * HEIC_CABAC_MIN_CTAS;
+    // HEIC_CABAC_MIN_CTAS CTAs of 8 warps are resident per SM: proportionally more when a CTA has fewer row slots
+    const uint32_t resident = resident_ctas > 0 ? (uint32_t)resident_ctas : (uint32_t)n_sm * (uint32_t)(HEIC_CABAC_MIN_CTAS * 8 / n_slots);
     if (group_counter && n_groups > resident && n_groups < 0xffff0u)
       cabac_kernel<32><<<resident, threads, smem, stream>>>(A, tabs, order, n_slots, n_groups, group_counter);
     else
