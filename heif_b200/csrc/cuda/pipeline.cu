@@ -111,6 +111,7 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
+  int probe_mix_k = 0, probe_mix_p = 0;  // measurement knob, see load()
   int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
   int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
   int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
@@ -325,6 +326,21 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   for (auto& kv : by_shape) {
     std::vector<uint32_t>& v = kv.second;
     std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tiles[a].bs_len > tiles[b].bs_len; });
+    if (ctx->probe_mix_k > 1 && ctx->probe_mix_p > 0) {
+      // Measurement knob (tools/cabac_divergence.py): a benchmark batch built from few distinct tiles puts copies of one
+      // tile into the 32 lanes of a warp.  Read blocks of k * p sorted entries (k runs of p copies) column by column, so
+      // that a warp holds k different tiles of neighbouring size instead.
+      const size_t k = (size_t)ctx->probe_mix_k, p = (size_t)ctx->probe_mix_p;
+      std::vector<uint32_t> w;
+      w.reserve(v.size());
+      for (size_t b0 = 0; b0 < v.size(); b0 += k * p) {
+        const size_t n = std::min(k * p, v.size() - b0), rows = (n + p - 1) / p;
+        for (size_t c = 0; c < p; c++)
+          for (size_t r = 0; r < rows; r++)
+            if (r * p + c < n) w.push_back(v[b0 + r * p + c]);
+      }
+      v.swap(w);
+    }
     const int wpp = std::get<0>(kv.first), wctb = std::get<1>(kv.first), hctb = std::get<2>(kv.first);
     CabacClass c;
     // with the two-CTU WPP lag at most ceil(wctb / 2) rows of a picture are in flight
@@ -585,6 +601,8 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
     c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
     c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
+    c->probe_mix_k = env_int("HEIC_B200_PROBE_MIX_K", 0);
+    c->probe_mix_p = env_int("HEIC_B200_PROBE_MIX_P", 0);
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;
