@@ -246,3 +246,38 @@ def test_gpu_unescape_matches_reference_vectors_and_host(decoder):
     # more removals in one NAL unit than the kernel's table: rejected, not mis-decoded
     with pytest.raises(H.HeicError):
         decoder.unescape(bytes([0, 0, 3]) * 2000)
+
+
+def test_corrupt_tiles_in_a_multi_group_batch(decoder, heic_file, oracle_rgb):
+    """Five CABAC groups (160 tiles) with corrupt tiles in different groups: under the thread-per-substream mapping the
+    two persistent CTAs hand groups over warp by warp, and a failed tile must neither stall that nor leak into the next
+    group handled by the same lanes."""
+    base = heic_file.primary
+    imgs, keep = [], []
+    rng = np.random.default_rng(3)
+    bad_of = {0: 5, 2: 40, 3: 17}  # image -> corrupted tile
+    for i in range(4):
+        img, tiles = permuted_image(base, list(range(48)))
+        if i in bad_of:
+            t = bad_of[i]
+            raw = bytearray(bytes(base.tiles[t].rbsp[: base.tiles[t].rbsp_len]))
+            off = base.tiles[t].header.slice_data_byte_offset
+            for j in range(off + 40 + 13 * i, len(raw)):
+                raw[j] = (raw[j] * 31 + 7 + i) & 0xFF
+            buf = (C.c_uint8 * len(raw)).from_buffer(raw)
+            tiles[t].rbsp = C.cast(buf, C.POINTER(K.u8))
+            keep.append(buf)
+        imgs.append(img)
+        keep.append(tiles)
+    out, rc, st = decoder.decode_grids(imgs, return_status=True)
+    assert rc == K.HEIC_E_BITSTREAM
+    for i in range(4):
+        for t in range(48):
+            if bad_of.get(i) == t:
+                assert st[i * 48 + t].code != 0
+                continue
+            assert st[i * 48 + t].code == 0, (i, t)
+            r, c = divmod(t, 8)
+            y0, x0 = r * 512, c * 512
+            assert np.array_equal(out[i, y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)],
+                                  oracle_rgb[y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)]), (i, t)
