@@ -392,7 +392,27 @@ def main():
         if any(st2[i].code != 0 for i in range(batch.n_tiles)):
             raise SystemExit("mixed-warp decode failed")
         mixed_ms = m0.elapsed_time(m1) / 2
+        # the end-to-end loop the same way (its chunks of 32 images hold 32 copies of every tile as well)
+        batch.close()
+        dec.close()
+        os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"] = "32", os.environ.get("HEIC_B200_PIPE_CHUNK", "32")
+        dec = H.HeicDecoder(device=local)
+        del os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"]
+        batch = dec.batch(images[:1])
+        for _ in range(2):
+            dec.decode_grids(images[:eb], out=out_np)
+        t0 = time.perf_counter()
+        prev = None
+        for k in range(e2e_steps):
+            job = dec.submit_grids(images[:eb], outs[k & 1])
+            if prev is not None:
+                dec.wait_job(prev)
+            prev = job
+        dec.wait_job(prev)
+        torch.cuda.synchronize()
+        mixed_e2e_s = (time.perf_counter() - t0) / e2e_steps
         mixed = {"value": round(n_img * MP_PER_IMAGE / (mixed_ms * 1e-3), 2), "unit": "MP/s", "ms_per_step": round(mixed_ms, 4),
+                 "e2e": round(eb * MP_PER_IMAGE / mixed_e2e_s, 2),
                  "cabac_ms": round(m1.elapsed_time(m2), 4),
                  "note": "same batch, resident, but every CABAC warp holds 32 different tiles of neighbouring size (no copies "
                          "of one tile in a warp, as in a batch of distinct photographs; includes the size spread of the "
