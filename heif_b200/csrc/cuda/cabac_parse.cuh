@@ -546,7 +546,16 @@ struct Parser {
   }
 
   // ---- 7.3.8.11 residual_coding + 9.3.4.2.4-7; writes TransCoeffLevel (raster n x n) to out -------
-  HEIC_HD int residual_coding(int log2, int c_idx, int pred_mode, int16_t* out) {
+  // Split into a prologue (transform_skip_flag, last significant position) and one call per 4x4 sub-block, so that the
+  // same code serves the nested walk (host) and the flat per-sub-block loop of the device (coding_tree_unit).
+  struct Rc {
+    int log2, c_idx, scan_idx, n, lg_sb, sb_w, sig_base, sig_off, last_sub_block, last_scan_pos;
+    int greater1_ctx, first_sub_block, tskip;
+    int i;          // next sub-block (scan order, counting down)
+    uint64_t csbf;  // coded_sub_block_flag, bit ys*8+xs
+    int16_t* out;
+  };
+  HEIC_HD void rc_begin(Rc& r, int log2, int c_idx, int pred_mode, int16_t* out) {
     const int n = 1 << log2;
     int tskip = 0;
     if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
@@ -584,114 +593,140 @@ HEIC_NO_UNROLL
     const int sig_base = CTX_SIG + (c_idx ? 27 : 0);
     // sigCtx offset for the non-4x4, non-DC case (9.3.4.2.5)
     const int sig_off = c_idx == 0 ? ((log2 == 3) ? (scan_idx == 0 ? 9 : 15) : 21) : ((log2 == 3) ? 9 : 12);
-    uint64_t csbf = 0;  // bit ys*8+xs
-    int greater1_ctx = 1, first_sub_block = 1;
-    for (int i = last_sub_block; i >= 0 && !err; i--) {
-      uint32_t sxy = scan_xy(scan_idx, lg_sb, i);
-      const int xs = (int)(sxy & 15u), ys = (int)(sxy >> 4);
-      int right = (xs < sb_w - 1) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1u) : 0;
-      int below = (ys < sb_w - 1) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1u) : 0;
-      int infer_sb_dc = 0, coded = 1;
-      if (i < last_sub_block && i > 0) {
-        coded = dec(CTX_CSBF + (c_idx ? 2 : 0) + (right | below));
-        infer_sb_dc = 1;
-      }
-      if (coded) csbf |= (uint64_t)1 << (ys * 8 + xs);
-      uint32_t sig = 0;
-      int n_start = 15;
-      if (i == last_sub_block) {
-        n_start = last_scan_pos - 1;
-        sig = 1u << last_scan_pos;
-      }
-      if (coded) {
-        const int prev_csbf = right | (below << 1);
-        // sigCtx (9.3.4.2.5) of all 16 scan positions of this sub-block as one word of nibbles + one additive term
-        const uint64_t nib = tabs()->sig_nib[log2 == 2 ? scan_idx : 3 + scan_idx * 4 + prev_csbf];
-        const int add = sig_base + (log2 == 2 ? 0 : ((c_idx == 0 && (xs | ys)) ? 3 : 0) + sig_off);
-        if (n_start > 0) sig |= sig_run(add, nib, n_start);
-        if (n_start >= 0) {
-          if (infer_sb_dc && sig == 0) {
-            sig = 1u;  // inferred DC of a coded sub-block with no other significant coefficient
-          } else {
-            // the DC coefficient of the whole block has its own context (sigCtx 0)
-            const int ctx0 = (log2 > 2 && i == 0) ? sig_base : add + (int)(nib & 15u);
-            if (dec(ctx0)) sig |= 1u;
-          }
+    r.log2 = log2;
+    r.c_idx = c_idx;
+    r.scan_idx = scan_idx;
+    r.n = n;
+    r.lg_sb = lg_sb;
+    r.sb_w = sb_w;
+    r.sig_base = sig_base;
+    r.sig_off = sig_off;
+    r.last_sub_block = last_sub_block;
+    r.last_scan_pos = last_scan_pos;
+    r.greater1_ctx = 1;
+    r.first_sub_block = 1;
+    r.tskip = tskip;
+    r.i = last_sub_block;
+    r.csbf = 0;
+    r.out = out;
+  }
+  HEIC_HD void rc_subblock(Rc& r) {  // sub-block r.i
+    const int log2 = r.log2, c_idx = r.c_idx, scan_idx = r.scan_idx, n = r.n, lg_sb = r.lg_sb, sb_w = r.sb_w;
+    const int sig_base = r.sig_base, sig_off = r.sig_off, last_sub_block = r.last_sub_block, last_scan_pos = r.last_scan_pos;
+    const int i = r.i;
+    int16_t* out = r.out;
+    uint64_t& csbf = r.csbf;
+    int& greater1_ctx = r.greater1_ctx;
+    int& first_sub_block = r.first_sub_block;
+    uint32_t sxy = scan_xy(scan_idx, lg_sb, i);
+    const int xs = (int)(sxy & 15u), ys = (int)(sxy >> 4);
+    int right = (xs < sb_w - 1) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1u) : 0;
+    int below = (ys < sb_w - 1) ? (int)((csbf >> ((ys + 1) * 8 + xs)) & 1u) : 0;
+    int infer_sb_dc = 0, coded = 1;
+    if (i < last_sub_block && i > 0) {
+      coded = dec(CTX_CSBF + (c_idx ? 2 : 0) + (right | below));
+      infer_sb_dc = 1;
+    }
+    if (coded) csbf |= (uint64_t)1 << (ys * 8 + xs);
+    uint32_t sig = 0;
+    int n_start = 15;
+    if (i == last_sub_block) {
+      n_start = last_scan_pos - 1;
+      sig = 1u << last_scan_pos;
+    }
+    if (coded) {
+      const int prev_csbf = right | (below << 1);
+      // sigCtx (9.3.4.2.5) of all 16 scan positions of this sub-block as one word of nibbles + one additive term
+      const uint64_t nib = tabs()->sig_nib[log2 == 2 ? scan_idx : 3 + scan_idx * 4 + prev_csbf];
+      const int add = sig_base + (log2 == 2 ? 0 : ((c_idx == 0 && (xs | ys)) ? 3 : 0) + sig_off);
+      if (n_start > 0) sig |= sig_run(add, nib, n_start);
+      if (n_start >= 0) {
+        if (infer_sb_dc && sig == 0) {
+          sig = 1u;  // inferred DC of a coded sub-block with no other significant coefficient
+        } else {
+          // the DC coefficient of the whole block has its own context (sigCtx 0)
+          const int ctx0 = (log2 > 2 && i == 0) ? sig_base : add + (int)(nib & 15u);
+          if (dec(ctx0)) sig |= 1u;
         }
-      }
-      if (!sig) continue;
-      // 9.3.4.2.6 / 9.3.4.2.7: up to 8 greater1 flags, one greater2 flag
-      int ctx_set = (i > 0 && c_idx == 0) ? 2 : 0;
-      if (!first_sub_block && greater1_ctx == 0) ctx_set++;
-      first_sub_block = 0;
-      greater1_ctx = 1;
-      uint32_t g1 = 0;
-      int last_g1_pos = -1;
-      const int last_sig = 31 - HEIC_CLZ(sig);
-      const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
-#if defined(HEIC_CABAC_OUTLINED)
-      {
-        const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0);
-        e = r.e;
-        g1 = r.v;
-        greater1_ctx = r.bad & 0xff;
-        last_g1_pos = (r.bad >> 8) - 1;
-      }
-#else
-      {
-        uint32_t m = sig;
-        int num_g1 = 0;
-        while (m && num_g1 < 8) {
-          int k = 31 - HEIC_CLZ(m);
-          m &= ~(1u << k);
-          int f = dec(CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2) + greater1_ctx);
-          num_g1++;
-          if (f) {
-            g1 |= 1u << k;
-            greater1_ctx = 0;
-            if (last_g1_pos < 0) last_g1_pos = k;
-          } else if (greater1_ctx > 0 && greater1_ctx < 3) {
-            greater1_ctx++;
-          }
-        }
-      }
-#endif
-      const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
-      int g2 = 0;
-      if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
-      // coeff_sign_flag: one bypass bin per coefficient in scan order (none for the hidden one, which comes last):
-      // read them in one go, most significant bit = first coefficient
-      const int n_sign = HEIC_POPC(sig) - (sign_hidden ? 1 : 0);
-      uint32_t sign_bits = n_sign ? fl_bypass(n_sign) << (32 - n_sign) : 0u;
-      int num_sig = 0, sum_abs = 0, rice = 0;
-      uint32_t m = sig;
-      while (m) {
-        int k = 31 - HEIC_CLZ(m);
-        m &= ~(1u << k);
-        int base = 1 + (int)((g1 >> k) & 1u) + ((k == last_g1_pos) ? g2 : 0);
-        int abs_level = base;
-        if (base == ((num_sig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
-          uint32_t rem = coeff_abs_level_remaining(rice);
-          if (rem > 32768u) {
-            fail(-3);
-            return tskip;
-          }
-          abs_level = base + (int)rem;
-          if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
-        }
-        int v = (sign_bits >> 31) ? -abs_level : abs_level;
-        sign_bits <<= 1;
-        if (sign_hidden) {
-          sum_abs += abs_level;
-          if (k == first_sig && (sum_abs & 1)) v = -v;
-        }
-        uint32_t pxy = scan_xy(scan_idx, 2, k);
-        int xc = (xs << 2) + (int)(pxy & 15u), yc = (ys << 2) + (int)(pxy >> 4);
-        out[yc * n + xc] = (int16_t)clip3i(-32768, 32767, v);
-        num_sig++;
       }
     }
-    return tskip;
+    if (!sig) return;
+    // 9.3.4.2.6 / 9.3.4.2.7: up to 8 greater1 flags, one greater2 flag
+    int ctx_set = (i > 0 && c_idx == 0) ? 2 : 0;
+    if (!first_sub_block && greater1_ctx == 0) ctx_set++;
+    first_sub_block = 0;
+    greater1_ctx = 1;
+    uint32_t g1 = 0;
+    int last_g1_pos = -1;
+    const int last_sig = 31 - HEIC_CLZ(sig);
+    const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
+#if defined(HEIC_CABAC_OUTLINED)
+    {
+      const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0);
+      e = r.e;
+      g1 = r.v;
+      greater1_ctx = r.bad & 0xff;
+      last_g1_pos = (r.bad >> 8) - 1;
+    }
+#else
+    {
+      uint32_t m = sig;
+      int num_g1 = 0;
+      while (m && num_g1 < 8) {
+        int k = 31 - HEIC_CLZ(m);
+        m &= ~(1u << k);
+        int f = dec(CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2) + greater1_ctx);
+        num_g1++;
+        if (f) {
+          g1 |= 1u << k;
+          greater1_ctx = 0;
+          if (last_g1_pos < 0) last_g1_pos = k;
+        } else if (greater1_ctx > 0 && greater1_ctx < 3) {
+          greater1_ctx++;
+        }
+      }
+    }
+#endif
+    const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
+    int g2 = 0;
+    if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
+    // coeff_sign_flag: one bypass bin per coefficient in scan order (none for the hidden one, which comes last):
+    // read them in one go, most significant bit = first coefficient
+    const int n_sign = HEIC_POPC(sig) - (sign_hidden ? 1 : 0);
+    uint32_t sign_bits = n_sign ? fl_bypass(n_sign) << (32 - n_sign) : 0u;
+    int num_sig = 0, sum_abs = 0, rice = 0;
+    uint32_t m = sig;
+    while (m) {
+      int k = 31 - HEIC_CLZ(m);
+      m &= ~(1u << k);
+      int base = 1 + (int)((g1 >> k) & 1u) + ((k == last_g1_pos) ? g2 : 0);
+      int abs_level = base;
+      if (base == ((num_sig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
+        uint32_t rem = coeff_abs_level_remaining(rice);
+        if (rem > 32768u) {
+          fail(-3);
+          return;
+        }
+        abs_level = base + (int)rem;
+        if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
+      }
+      int v = (sign_bits >> 31) ? -abs_level : abs_level;
+      sign_bits <<= 1;
+      if (sign_hidden) {
+        sum_abs += abs_level;
+        if (k == first_sig && (sum_abs & 1)) v = -v;
+      }
+      uint32_t pxy = scan_xy(scan_idx, 2, k);
+      int xc = (xs << 2) + (int)(pxy & 15u), yc = (ys << 2) + (int)(pxy >> 4);
+      out[yc * n + xc] = (int16_t)clip3i(-32768, 32767, v);
+      num_sig++;
+    }
+  }
+  HEIC_HD int residual_coding(int log2, int c_idx, int pred_mode, int16_t* out) {
+    Rc r;
+    rc_begin(r, log2, c_idx, pred_mode, out);
+    for (; r.i >= 0 && !err; r.i--) rc_subblock(r);
+    return r.tskip;
   }
 
   // ---- 8.6.1 ------------------------------------------------------------------------------------
