@@ -742,16 +742,26 @@ HEIC_NO_UNROLL
   }
 
   // ---- 7.3.8.10 transform_unit ------------------------------------------------------------------
-  // z4: z-order index of the TU's 4x4 origin inside its CTB; ctb_addr: raster CTB address
-  HEIC_HD void transform_unit(int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr,
-                              uint32_t ctb_addr, uint32_t z4) {
+  // z4: z-order index of the TU's 4x4 origin inside its CTB; ctb_addr: raster CTB address.  Split into the part before
+  // the residuals (tu_begin), the choice of a component's residual block (tu_component) and the tu_map record (tu_end).
+  struct Tu {
+    int log2, log2c, luma_mode, has_chroma, cbf_luma, cbf_cb, cbf_cr;
+    uint32_t ti, ts;  // tu_map index; transform_skip_flag of the three components
+    size_t off_c;     // chroma coefficient offset
+  };
+  HEIC_HD void tu_begin(Tu& t, int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr, uint32_t ctb_addr,
+                        uint32_t z4) {
     const int pb_shift = part_nxn ? cu_log2 - 1 : cu_log2;
     const int pu_idx = (((x0 - cu_x) >> pb_shift) & 1) | ((((y0 - cu_y) >> pb_shift) & 1) << 1);
-    const int luma_mode = (int)((pu_modes >> (8 * pu_idx)) & 0xffu);
-    const int has_chroma = pp->chroma && (log2 > 2 || blk_idx == 3);
-    const int log2c = log2 > 2 ? log2 - 1 : 2;
+    t.luma_mode = (int)((pu_modes >> (8 * pu_idx)) & 0xffu);
+    t.has_chroma = pp->chroma && (log2 > 2 || blk_idx == 3);
+    t.log2 = log2;
+    t.log2c = log2 > 2 ? log2 - 1 : 2;
     const int any_cbf = cbf_luma | cbf_cb | cbf_cr;  // 7.3.8.10: parent-inherited chroma cbfs count for blkIdx 0..2 too
-    if (!has_chroma) cbf_cb = cbf_cr = 0;
+    if (!t.has_chroma) cbf_cb = cbf_cr = 0;
+    t.cbf_luma = cbf_luma;
+    t.cbf_cb = cbf_cb;
+    t.cbf_cr = cbf_cr;
     if (any_cbf && pp->cu_qp_delta_enabled && !is_cu_qp_delta_coded) {
       // cu_qp_delta_abs: prefix TR cMax 5 (bin 0 ctx 0, bins 1-4 ctx 1) + EG0 suffix (decoder.rs:263-284)
       int v = 0;
@@ -763,24 +773,41 @@ HEIC_NO_UNROLL
       if (cu_qp_delta_val < -26 || cu_qp_delta_val > 25) fail(-3);
       qp_y = (qp_y_pred + cu_qp_delta_val + 52) % 52;
     }
-    if (err) return;
     const int ctb4 = 1 << (pp->log2_ctb - 2);
-    const uint32_t ti = ctb_addr * (uint32_t)(ctb4 * ctb4) + z4;
+    t.ti = ctb_addr * (uint32_t)(ctb4 * ctb4) + z4;
+    t.off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
+    t.ts = 0;
+  }
+  // residual block of component c: false when its cbf is 0, else the arguments of rc_begin
+  HEIC_HD bool tu_component(const Tu& t, int c, int& log2, int& pred_mode, int16_t*& dst) const {
+    const int cbf = c == 0 ? t.cbf_luma : (c == 1 ? t.cbf_cb : t.cbf_cr);
+    if (!cbf) return false;
+    dst = c == 0 ? coeff0 + (size_t)t.ti * 16 : (c == 1 ? coeff1 : coeff2) + t.off_c;
+    log2 = c ? t.log2c : t.log2;
+    pred_mode = c ? chroma_mode : t.luma_mode;
+    return true;
+  }
+  HEIC_HD void tu_end(const Tu& t) {
+    const int ts0 = (int)(t.ts & 1u), ts1 = (int)((t.ts >> 1) & 1u), ts2 = (int)((t.ts >> 2) & 1u);
+    tu_map[t.ti] = 1u | ((uint32_t)(t.log2 - 2) << 1) | ((uint32_t)t.cbf_luma << 3) | ((uint32_t)t.cbf_cb << 4) |
+                   ((uint32_t)t.cbf_cr << 5) | ((uint32_t)t.has_chroma << 6) | ((uint32_t)t.luma_mode << 7) |
+                   ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |
+                   ((uint32_t)ts1 << 26) | ((uint32_t)ts2 << 27);
+  }
+  HEIC_HD void transform_unit(int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr,
+                              uint32_t ctb_addr, uint32_t z4) {
+    Tu t;
+    tu_begin(t, x0, y0, log2, blk_idx, cbf_luma, cbf_cb, cbf_cr, ctb_addr, z4);
+    if (err) return;
     // one residual_coding call site for the three components keeps the kernel's instruction footprint small
-    const size_t off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
-    uint32_t ts = 0;
 HEIC_NO_UNROLL
     for (int c = 0; c < 3; c++) {
-      const int cbf = c == 0 ? cbf_luma : (c == 1 ? cbf_cb : cbf_cr);
-      if (!cbf) continue;
-      int16_t* dst = c == 0 ? coeff0 + (size_t)ti * 16 : (c == 1 ? coeff1 : coeff2) + off_c;
-      ts |= (uint32_t)residual_coding(c ? log2c : log2, c, c ? chroma_mode : luma_mode, dst) << c;
+      int lg, pm;
+      int16_t* dst;
+      if (!tu_component(t, c, lg, pm, dst)) continue;
+      t.ts |= (uint32_t)residual_coding(lg, c, pm, dst) << c;
     }
-    const int ts0 = (int)(ts & 1u), ts1 = (int)((ts >> 1) & 1u), ts2 = (int)((ts >> 2) & 1u);
-    tu_map[ti] = 1u | ((uint32_t)(log2 - 2) << 1) | ((uint32_t)cbf_luma << 3) | ((uint32_t)cbf_cb << 4) |
-                 ((uint32_t)cbf_cr << 5) | ((uint32_t)has_chroma << 6) | ((uint32_t)luma_mode << 7) |
-                 ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |
-                 ((uint32_t)ts1 << 26) | ((uint32_t)ts2 << 27);
+    tu_end(t);
   }
 
   // ---- 7.3.8.8 transform_tree, walked iteratively in z-order over the CU's 4x4 blocks -----------
