@@ -794,10 +794,63 @@ HEIC_NO_UNROLL
                    ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |
                    ((uint32_t)ts1 << 26) | ((uint32_t)ts2 << 27);
   }
-  HEIC_HD void transform_unit(int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr,
-                              uint32_t ctb_addr, uint32_t z4) {
-    Tu t;
-    tu_begin(t, x0, y0, log2, blk_idx, cbf_luma, cbf_cb, cbf_cr, ctb_addr, z4);
+  // ---- 7.3.8.8 transform_tree, walked iteratively in z-order over the CU's 4x4 blocks -----------
+  struct Tt {
+    uint32_t z, n4;             // next 4x4 block of the CU in z-order, their number
+    uint32_t cb_mask, cr_mask;  // bit d: cbf_cb / cbf_cr of the current node at trafoDepth d
+    uint32_t step;              // 4x4 blocks covered by the leaf found last
+  };
+  HEIC_HD void tt_begin(Tt& t) const {
+    t.z = 0;
+    t.n4 = 1u << (2 * (cu_log2 - 2));
+    t.cb_mask = t.cr_mask = 0;
+    t.step = 0;
+  }
+  // Descends from the largest block whose origin is t.z to its leaf (split_transform_flag, cbf_cb, cbf_cr, cbf_luma)
+  // and starts that transform unit.
+  HEIC_HD void tt_leaf(Tt& t, Tu& tu, uint32_t ctb_addr, uint32_t z4_cu) {
+    const int intra_split = part_nxn;
+    const int max_depth = pp->max_trafo_depth_intra + intra_split;
+    const uint32_t z = t.z;
+    int lvl = cu_log2 - 2;  // largest block whose origin is z
+    if (z) {
+      int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
+      if (tz < lvl) lvl = tz;
+    }
+    int log2 = lvl + 2;
+    for (;;) {
+      const int depth = cu_log2 - log2;
+      int split;
+      if (log2 <= pp->log2_max_tb && log2 > pp->log2_min_tb && depth < max_depth && !(intra_split && depth == 0))
+        split = dec(CTX_SPLIT_TRANSFORM + 5 - log2);
+      else
+        split = (log2 > pp->log2_max_tb) || (intra_split && depth == 0);
+      int cbf_cb = 0, cbf_cr = 0;
+      if (pp->chroma) {
+        int par_cb = depth ? (int)((t.cb_mask >> (depth - 1)) & 1u) : 1;
+        int par_cr = depth ? (int)((t.cr_mask >> (depth - 1)) & 1u) : 1;
+        if (log2 > 2) {
+          if (par_cb) cbf_cb = dec(CTX_CBF_CHROMA + depth);
+          if (par_cr) cbf_cr = dec(CTX_CBF_CHROMA + depth);
+        } else {  // inferred from the parent when log2TrafoSize == 2
+          cbf_cb = depth ? par_cb : 0;
+          cbf_cr = depth ? par_cr : 0;
+        }
+      }
+      t.cb_mask = (t.cb_mask & ~(1u << depth)) | ((uint32_t)cbf_cb << depth);
+      t.cr_mask = (t.cr_mask & ~(1u << depth)) | ((uint32_t)cbf_cr << depth);
+      if (!split) {
+        int cbf_luma = dec(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));  // always present for intra CUs
+        int x0 = cu_x + (int)(compact1by1(z) << 2), y0 = cu_y + (int)(compact1by1(z >> 1) << 2);
+        tu_begin(tu, x0, y0, log2, (int)(z & 3u), cbf_luma, cbf_cb, cbf_cr, ctb_addr, z4_cu + z);
+        break;
+      }
+      log2--;
+    }
+    t.step = 1u << (2 * (log2 - 2));
+  }
+  // residuals of the transform unit just started, then its tu_map record (the nested form of the device's flat loop)
+  HEIC_HD void tu_residuals(Tu& t) {
     if (err) return;
     // one residual_coding call site for the three components keeps the kernel's instruction footprint small
 HEIC_NO_UNROLL
@@ -809,51 +862,14 @@ HEIC_NO_UNROLL
     }
     tu_end(t);
   }
-
-  // ---- 7.3.8.8 transform_tree, walked iteratively in z-order over the CU's 4x4 blocks -----------
   HEIC_HD void transform_tree(uint32_t ctb_addr, uint32_t z4_cu) {
-    const int intra_split = part_nxn;
-    const int max_depth = pp->max_trafo_depth_intra + intra_split;
-    const uint32_t n4 = 1u << (2 * (cu_log2 - 2));
-    uint32_t cb_mask = 0, cr_mask = 0;  // bit d: cbf_cb / cbf_cr of the current node at trafoDepth d
-    uint32_t z = 0;
-    while (z < n4 && !err) {
-      int lvl = cu_log2 - 2;  // largest block whose origin is z
-      if (z) {
-        int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
-        if (tz < lvl) lvl = tz;
-      }
-      int log2 = lvl + 2;
-      for (;;) {
-        const int depth = cu_log2 - log2;
-        int split;
-        if (log2 <= pp->log2_max_tb && log2 > pp->log2_min_tb && depth < max_depth && !(intra_split && depth == 0))
-          split = dec(CTX_SPLIT_TRANSFORM + 5 - log2);
-        else
-          split = (log2 > pp->log2_max_tb) || (intra_split && depth == 0);
-        int cbf_cb = 0, cbf_cr = 0;
-        if (pp->chroma) {
-          int par_cb = depth ? (int)((cb_mask >> (depth - 1)) & 1u) : 1;
-          int par_cr = depth ? (int)((cr_mask >> (depth - 1)) & 1u) : 1;
-          if (log2 > 2) {
-            if (par_cb) cbf_cb = dec(CTX_CBF_CHROMA + depth);
-            if (par_cr) cbf_cr = dec(CTX_CBF_CHROMA + depth);
-          } else {  // inferred from the parent when log2TrafoSize == 2
-            cbf_cb = depth ? par_cb : 0;
-            cbf_cr = depth ? par_cr : 0;
-          }
-        }
-        cb_mask = (cb_mask & ~(1u << depth)) | ((uint32_t)cbf_cb << depth);
-        cr_mask = (cr_mask & ~(1u << depth)) | ((uint32_t)cbf_cr << depth);
-        if (!split) {
-          int cbf_luma = dec(CTX_CBF_LUMA + (depth == 0 ? 1 : 0));  // always present for intra CUs
-          int x0 = cu_x + (int)(compact1by1(z) << 2), y0 = cu_y + (int)(compact1by1(z >> 1) << 2);
-          transform_unit(x0, y0, log2, (int)(z & 3u), cbf_luma, cbf_cb, cbf_cr, ctb_addr, z4_cu + z);
-          break;
-        }
-        log2--;
-      }
-      z += 1u << (2 * (log2 - 2));
+    Tt t;
+    tt_begin(t);
+    while (t.z < t.n4 && !err) {
+      Tu tu;
+      tt_leaf(t, tu, ctb_addr, z4_cu);
+      tu_residuals(tu);
+      t.z += t.step;
     }
   }
 
