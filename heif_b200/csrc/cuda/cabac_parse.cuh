@@ -909,7 +909,8 @@ HEIC_NO_UNROLL
   }
 
   // ---- 7.3.8.5 coding_unit (I slice) -------------------------------------------------------------
-  HEIC_HD void coding_unit(int x0, int y0, int log2, uint32_t ctb_addr, uint32_t z4_cu) {
+  // prediction part of the CU (everything before its transform tree)
+  HEIC_HD void cu_begin(int x0, int y0, int log2) {
     const int n = 1 << log2;
     cu_x = x0;
     cu_y = y0;
@@ -960,11 +961,19 @@ HEIC_NO_UNROLL
         chroma_mode = (m == luma) ? 34 : m;
       }
     }
-    transform_tree(ctb_addr, z4_cu);
+  }
+  HEIC_HD void cu_end() {
     // QpY of the CU (8.6.1): CuQpDeltaVal decoded anywhere inside the CU applies to all of it
-    for (int yy = y0 >> 3; yy < (y0 + n) >> 3; yy++)
-      for (int xx = x0 >> 3; xx < (x0 + n) >> 3; xx++) qp_map[yy * pp->w8 + xx] = (uint8_t)qp_y;
+    const int n = 1 << cu_log2;
+    for (int yy = cu_y >> 3; yy < (cu_y + n) >> 3; yy++)
+      for (int xx = cu_x >> 3; xx < (cu_x + n) >> 3; xx++) qp_map[yy * pp->w8 + xx] = (uint8_t)qp_y;
     last_qp_y = qp_y;
+  }
+  HEIC_HD void coding_unit(int x0, int y0, int log2, uint32_t ctb_addr, uint32_t z4_cu) {
+    cu_begin(x0, y0, log2);
+    if (err) return;
+    transform_tree(ctb_addr, z4_cu);
+    cu_end();
   }
 
   // ---- 7.3.8.4 coding_quadtree (todo!() at slice.rs:253-255), iterative z-order walk of one CTB ---
