@@ -977,54 +977,146 @@ HEIC_NO_UNROLL
   }
 
   // ---- 7.3.8.4 coding_quadtree (todo!() at slice.rs:253-255), iterative z-order walk of one CTB ---
+  // One step of the walk: from the minimum-size block z (z-order inside the CTB) descend through split_cu_flag to the
+  // coding unit that starts there.  False: the quadrant lies outside the picture and was skipped (z advanced).
+  HEIC_HD bool ctu_next_cu(uint32_t& z, int x_ctb, int y_ctb, int& x0_out, int& y0_out, int& log2_out) {
+    const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
+    const int max_lvl = log2_ctb - log2_min_cb;
+    int lvl = max_lvl;
+    if (z) {
+      int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
+      if (tz < lvl) lvl = tz;
+    }
+    int log2 = log2_min_cb + lvl;
+    const int x0 = x_ctb + (int)(compact1by1(z) << log2_min_cb), y0 = y_ctb + (int)(compact1by1(z >> 1) << log2_min_cb);
+    if (x0 >= pp->w || y0 >= pp->h) {  // quadrant entirely outside the picture: not coded
+      z += 1u << (2 * lvl);
+      return false;
+    }
+    for (;;) {
+      const int depth = log2_ctb - log2, n = 1 << log2;
+      int split;
+      if (x0 + n <= pp->w && y0 + n <= pp->h && log2 > log2_min_cb) {
+        int inc = 0;
+        if (x0 > 0 && ct_depth[(y0 >> 3) * pp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
+        if (y0 > 0 && ct_depth[((y0 - 1) >> 3) * pp->w8 + (x0 >> 3)] > depth) inc++;
+        split = dec(CTX_SPLIT_CU + inc);
+      } else {
+        split = log2 > log2_min_cb;
+      }
+      if (pp->cu_qp_delta_enabled && log2 >= pp->log2_min_cu_qp_delta_size) {
+        is_cu_qp_delta_coded = 0;
+        cu_qp_delta_val = 0;
+      }
+      if (!split) break;
+      log2--;
+    }
+    {
+      const int depth = log2_ctb - log2, b8 = 1 << (log2 - 3), x8 = x0 >> 3, y8 = y0 >> 3;
+      for (int j = 0; j < b8; j++) ct_depth[(y8 + j) * pp->w8 + x8 + b8 - 1] = (uint8_t)depth;
+      for (int j = 0; j < b8 - 1; j++) ct_depth[(y8 + b8 - 1) * pp->w8 + x8 + j] = (uint8_t)depth;
+    }
+    x0_out = x0;
+    y0_out = y0;
+    log2_out = log2;
+    return true;
+  }
+
+#if defined(HEIC_CABAC_FLAT)
+  // EXPERIMENT, off by default (-DHEIC_CABAC_FLAT): the CTU walked as ONE loop whose iteration is "advance to the next
+  // coded 4x4 sub-block, then decode it", so that lanes of a warp holding 32 different pictures meet at every sub-block
+  // instead of at the end of every loop level of the nested form (below).  Bins are consumed in exactly the order of the
+  // nested form (tests/test_emul_parser.py runs both).  Measured on B200 it LOSES: 65.4 vs 58.9 ms per 592 images with
+  // copies of one tile in a warp and 427 vs 255 ms with 32 different tiles per warp -- the serialised header branches of
+  // the advance loop run once per sub-block for the whole warp, which costs more than the loop-level waits it removes.
   HEIC_HD void coding_tree_unit(int rx, int ry) {
     const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
     const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
     const int x_ctb = rx << log2_ctb, y_ctb = ry << log2_ctb;
     if (!pp->cu_qp_delta_enabled) qp_y = tp->slice_qp;
     if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
-    const int max_lvl = log2_ctb - log2_min_cb;
-    const uint32_t n_min = 1u << (2 * max_lvl);
+    const uint32_t n_min = 1u << (2 * (log2_ctb - log2_min_cb));
+    enum { ST_CU, ST_TT, ST_COMP, ST_SB, ST_DONE };
+    int st = ST_CU, comp = 0;
+    uint32_t z = 0, z4_cu = 0;
+    Tt tt;
+    Tu tu;
+    Rc rc;
+    tt.z = tt.n4 = tt.cb_mask = tt.cr_mask = tt.step = 0;
+    for (;;) {
+      // ---- advance: everything between two sub-blocks ----
+      HEIC_NO_UNROLL
+      while (st != ST_SB && st != ST_DONE) {
+        if (err) {
+          st = ST_DONE;
+        } else if (st == ST_CU) {
+          if (z >= n_min) {
+            st = ST_DONE;
+          } else {
+            int x0, y0, log2;
+            if (ctu_next_cu(z, x_ctb, y_ctb, x0, y0, log2)) {
+              z4_cu = z << (2 * (log2_min_cb - 2));
+              z += 1u << (2 * (log2 - log2_min_cb));
+              cu_begin(x0, y0, log2);
+              tt_begin(tt);
+              st = ST_TT;
+            }
+          }
+        } else if (st == ST_TT) {
+          if (tt.z >= tt.n4) {
+            cu_end();
+            st = ST_CU;
+          } else {
+            tt_leaf(tt, tu, ctb_addr, z4_cu);
+            comp = 0;
+            st = ST_COMP;
+          }
+        } else {  // ST_COMP: next component of the transform unit with a residual
+          if (comp == 3) {
+            tu_end(tu);
+            tt.z += tt.step;
+            st = ST_TT;
+          } else {
+            int lg, pm;
+            int16_t* dst;
+            if (tu_component(tu, comp, lg, pm, dst)) {
+              rc_begin(rc, lg, comp, pm, dst);
+              st = ST_SB;
+            } else {
+              comp++;
+            }
+          }
+        }
+      }
+      if (st == ST_DONE || err) break;
+      // ---- one sub-block, all lanes that have one ----
+      rc_subblock(rc);
+      rc.i--;
+      if (rc.i < 0 || err) {
+        tu.ts |= (uint32_t)rc.tskip << comp;
+        comp++;
+        st = ST_COMP;
+      }
+    }
+  }
+#else
+  HEIC_HD void coding_tree_unit(int rx, int ry) {
+    const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
+    const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
+    const int x_ctb = rx << log2_ctb, y_ctb = ry << log2_ctb;
+    if (!pp->cu_qp_delta_enabled) qp_y = tp->slice_qp;
+    if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
+    const uint32_t n_min = 1u << (2 * (log2_ctb - log2_min_cb));
     uint32_t z = 0;
     while (z < n_min && !err) {
-      int lvl = max_lvl;
-      if (z) {
-        int tz = (31 - HEIC_CLZ(z & (0u - z))) >> 1;
-        if (tz < lvl) lvl = tz;
-      }
-      int log2 = log2_min_cb + lvl;
-      const int x0 = x_ctb + (int)(compact1by1(z) << log2_min_cb), y0 = y_ctb + (int)(compact1by1(z >> 1) << log2_min_cb);
-      if (x0 >= pp->w || y0 >= pp->h) {  // quadrant entirely outside the picture: not coded
-        z += 1u << (2 * lvl);
-        continue;
-      }
-      for (;;) {
-        const int depth = log2_ctb - log2, n = 1 << log2;
-        int split;
-        if (x0 + n <= pp->w && y0 + n <= pp->h && log2 > log2_min_cb) {
-          int inc = 0;
-          if (x0 > 0 && ct_depth[(y0 >> 3) * pp->w8 + ((x0 - 1) >> 3)] > depth) inc++;
-          if (y0 > 0 && ct_depth[((y0 - 1) >> 3) * pp->w8 + (x0 >> 3)] > depth) inc++;
-          split = dec(CTX_SPLIT_CU + inc);
-        } else {
-          split = log2 > log2_min_cb;
-        }
-        if (pp->cu_qp_delta_enabled && log2 >= pp->log2_min_cu_qp_delta_size) {
-          is_cu_qp_delta_coded = 0;
-          cu_qp_delta_val = 0;
-        }
-        if (!split) break;
-        log2--;
-      }
-      {
-        const int depth = log2_ctb - log2, b8 = 1 << (log2 - 3), x8 = x0 >> 3, y8 = y0 >> 3;
-        for (int j = 0; j < b8; j++) ct_depth[(y8 + j) * pp->w8 + x8 + b8 - 1] = (uint8_t)depth;
-        for (int j = 0; j < b8 - 1; j++) ct_depth[(y8 + b8 - 1) * pp->w8 + x8 + j] = (uint8_t)depth;
-      }
-      coding_unit(x0, y0, log2, ctb_addr, z << (2 * (log2_min_cb - 2)));
+      int x0, y0, log2;
+      const uint32_t z_cu = z;
+      if (!ctu_next_cu(z, x_ctb, y_ctb, x0, y0, log2)) continue;
+      coding_unit(x0, y0, log2, ctb_addr, z_cu << (2 * (log2_min_cb - 2)));
       z += 1u << (2 * (log2 - log2_min_cb));
     }
   }
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------

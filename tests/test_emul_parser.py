@@ -13,10 +13,12 @@ from oracle import oracle_py as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.fixture(scope="module")
-def emul():
+# "flat" is the device's per-sub-block CTU loop (HEIC_CABAC_FLAT in cabac_parse.cuh), "nested" the recursive-descent form
+@pytest.fixture(scope="module", params=["nested", "flat"])
+def emul(request):
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emul")])
-    lib = C.CDLL(os.path.join(HERE, "emul", "_build", "libcabac_emul.so"))
+    name = "libcabac_emul.so" if request.param == "nested" else "libcabac_emul_flat.so"
+    lib = C.CDLL(os.path.join(HERE, "emul", "_build", name))
     lib.emul_parse_picture.argtypes = ([C.POINTER(K.Sps), C.POINTER(K.Pps), C.POINTER(K.SliceHeader), C.c_void_p, C.c_uint32]
                                        + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)] * 2 + [C.c_int])
     return lib
