@@ -177,10 +177,44 @@ struct Engine {
     refill();
     return 0;
   }
+  // ---- several bypass bins per step -------------------------------------------------------------------------
+  // k bypass bins in a row are the long division of (ivlOffset * 2^k + next k bits) by ivlCurrRange: the quotient holds
+  // the bins (first bin = most significant bit), the remainder is the new ivlOffset.  And the first j bins of the k-bin
+  // quotient are the j-bin quotient (floor(floor(X / r) / 2^m) == floor(floor(X / 2^m) / r)), so a unary prefix can be
+  // decoded speculatively and only the bins it really has are consumed.  k <= 7 <= nbits always holds after a refill;
+  // X < 510 * 2^7 fits a float exactly, the estimate of the quotient is off by at most one and is corrected.
+  HEIC_HD uint32_t bypass_quot(uint32_t X) const {
+#if defined(__CUDA_ARCH__)
+    uint32_t q = (uint32_t)__fdividef((float)X, (float)range);
+    const int r = (int)X - (int)(q * range);
+    if (r < 0) q--;
+    else if (r >= (int)range) q++;
+    return q;
+#else
+    return X / range;
+#endif
+  }
+  // consume the first j of the k bins whose numerator / quotient are X / Q; returns those j bins
+  HEIC_HD uint32_t bypass_take(uint32_t X, uint32_t Q, int k, int j) {
+    const uint32_t Xj = X >> (k - j), Qj = Q >> (k - j);
+    val = ((Xj - Qj * range) << 22) | ((val << j) & 0x3fffffu);
+    nbits -= j;
+    bins += (uint32_t)j;
+    refill();
+    return Qj;
+  }
+  HEIC_HD uint32_t bypass_bins(int k) {  // 1 <= k <= 7
+    const uint32_t X = val >> (22 - k);
+    return bypass_take(X, bypass_quot(X), k, k);
+  }
   HEIC_HD uint32_t fl_bypass(int n) {  // decoder.rs:152-164
     uint32_t v = 0;
     HEIC_NO_UNROLL
-    for (int i = 0; i < n; i++) v = (v << 1) | (uint32_t)bypass();
+    while (n > 0) {
+      const int k = n < 7 ? n : 7;
+      v = (v << k) | bypass_bins(k);
+      n -= k;
+    }
     return v;
   }
   HEIC_HD uint32_t tr_bypass(uint32_t cmax) {  // decoder.rs:166-190, cRiceParam 0
@@ -202,11 +236,20 @@ struct Engine {
     return (((1u << ones) - 1u) << k) + suffix;
   }
   HEIC_HD uint32_t coeff_abs_level_remaining(int rice, int& bad) {  // decoder.rs:224-261
-    uint32_t prefix = 0;
-    HEIC_NO_UNROLL
-    while (prefix < 4 && bypass()) prefix++;
-    if (prefix < 4) return (prefix << rice) + fl_bypass(rice);
-    return (4u << rice) + egk_bypass(rice + 1, bad);
+    // prefix (up to four ones and the closing zero) and, when it fits, the rice suffix bits from one division
+    const int k = 4 + (rice < 3 ? rice : 3);
+    const uint32_t X = val >> (22 - k), Q = bypass_quot(X);
+    const uint32_t top4 = Q >> (k - 4);
+    const int prefix = HEIC_CLZ(~(top4 << 28));  // leading ones of the four prefix bins
+    if (prefix >= 4) {
+      bypass_take(X, Q, k, 4);
+      return (4u << rice) + egk_bypass(rice + 1, bad);
+    }
+    int j = prefix + 1 + rice;
+    if (j <= k) return ((uint32_t)prefix << rice) + (bypass_take(X, Q, k, j) & ((1u << rice) - 1u));
+    // rice == 4 and three ones: the last suffix bit does not fit the seven-bin division
+    const uint32_t hi = bypass_take(X, Q, k, k) & 7u;
+    return ((uint32_t)prefix << rice) + ((hi << 1) | (uint32_t)bypass());
   }
 };
 
@@ -1039,10 +1082,9 @@ HEIC_NO_UNROLL
     enum { ST_CU, ST_TT, ST_COMP, ST_SB, ST_DONE };
     int st = ST_CU, comp = 0;
     uint32_t z = 0, z4_cu = 0;
-    Tt tt;
-    Tu tu;
-    Rc rc;
-    tt.z = tt.n4 = tt.cb_mask = tt.cr_mask = tt.step = 0;
+    Tt tt{};
+    Tu tu{};
+    Rc rc{};
     for (;;) {
       // ---- advance: everything between two sub-blocks ----
       HEIC_NO_UNROLL
