@@ -321,7 +321,8 @@ def main():
     cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
-    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, 64), args.batch)  # pinned host RGB: 2 x 36.6 MB per image per rank
+    # pinned host RGB: 2 x 36.6 MB per image per rank -> the images per call shrink with the rank count (37 GB pinned in all)
+    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, max(64, 512 // world)), args.batch)
     out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
@@ -331,7 +332,9 @@ def main():
     # overlap call k's device->host copy.  Every call carries all of its own copies; two pinned output buffers alternate.
     out2 = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     outs = [out_np, out2.numpy()]
-    for _ in range(2):
+    # warm-up: the library's 8 pipeline slots (32 images each) allocate their arenas on first use, so run enough calls to
+    # have touched every slot before the timed region
+    for _ in range(max(2, -(-8 * 32 // eb) + 1)):
         dec.decode_grids(images[:eb], out=out_np)
     barrier()
     e2e_steps = max(3, min(args.steps, 6))
