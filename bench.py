@@ -101,6 +101,26 @@ class ClockSampler:
 # CPU arm: the oracle port (oracle/hevc_oracle.c) on the host cores.  kind = "port": the reference is Rust,
 # there is no cargo/rustc in the image, and its slice decoder ends in todo!() anyway ("Oracle").
 # ---------------------------------------------------------------------------------------------------------
+def host_memory_available() -> int:
+    """Bytes of host memory this process may still use: MemAvailable, capped by the cgroup limit if there is one."""
+    avail = 64 << 30
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            m = open(lim).read().strip()
+            if m != "max" and int(m) < (1 << 60):
+                avail = min(avail, int(m) - int(open(cur).read().strip()))
+        except (OSError, ValueError):
+            pass
+    return max(avail, 0)
+
+
 def cpu_decode_images(heic_file, n_images: int, threads: int) -> float:
     """Decodes n_images x 48 tiles + colour/stitch with `threads` host threads; returns seconds."""
     from concurrent.futures import ThreadPoolExecutor
@@ -321,8 +341,12 @@ def main():
     cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
-    # pinned host RGB: 2 x 36.6 MB per image per rank -> the images per call shrink with the rank count (37 GB pinned in all)
-    eb = min(args.e2e_batch if world == 1 else min(args.e2e_batch, max(64, 512 // world)), args.batch)
+    # pinned host RGB: 2 x 36.6 MB per image per rank; all ranks together may pin a quarter of the host memory that is free
+    eb = min(args.e2e_batch, args.batch)
+    if world > 1:
+        fit = torch.tensor([int(0.4 * host_memory_available() / world / (2 * OUT_H * OUT_W * 3))], device="cuda", dtype=torch.int64)
+        dist.all_reduce(fit, op=dist.ReduceOp.MIN)  # the same call size on every rank
+        eb = max(32, min(eb, int(fit[0]) // 32 * 32))
     out = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     out_np = out.numpy()
     h2d = sum(images[i].tiles[t].rbsp_len for i in range(eb) for t in range(48)) + eb * 48 * (C.sizeof(H._capi.TileDesc) // 8)
