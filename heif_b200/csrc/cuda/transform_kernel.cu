@@ -235,90 +235,92 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, 
     int16_t* blk = item.blk;
     if (col == 0) blk_of[warp][k] = blk;
     const bool tskip = active && tu_tskip(item.w, item.cidx);
-    // ---- scaling + first (column) pass -------------------------------------------------------
+    // The two 1-D passes run as one loop; for N == 32 it is not unrolled, so the three butterfly variants exist once
+    // instead of twice (3.5 K instructions did not fit the instruction cache: stall_no_instruction 5.7 per issue).
     int x[N], y[N];
-    int nz_rows = 0;
-    // raw levels first: only the rows up to the last non-zero one (warp-uniform bound) are scaled afterwards
-#pragma unroll
-    for (int j = 0; j < N; j++) {
-      x[j] = active ? (int)blk[j * N + col] : 0;
-      nz_rows = x[j] ? j + 1 : nz_rows;
-    }
-    // extents of the non-zero coefficients, uniform over the warp so the butterfly variant is too
-    int nz1 = nz_rows;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) nz1 = max(nz1, __shfl_xor_sync(0xffffffffu, nz1, o));
-    const uint32_t col_mask = __ballot_sync(0xffffffffu, nz_rows > 0);
-    // highest non-zero column index + 1 within any block of the step
     int nz2 = 0;
+    constexpr int UNROLL = N == 32 ? 1 : 2;
+#pragma unroll UNROLL
+    for (int pass = 0; pass < 2; pass++) {
+      int nz;
+      if (pass == 0) {
+        // ---- scaling + first (column) pass -----------------------------------------------------
+        int nz_rows = 0;
+        // raw levels first: only the rows up to the last non-zero one (warp-uniform bound) are scaled afterwards
 #pragma unroll
-    for (int g = 0; g < K; g++) {
-      uint32_t mg = (col_mask >> (g * N)) & (N == 32 ? 0xffffffffu : ((1u << N) - 1u));
-      nz2 = max(nz2, 32 - __clz(mg));
-    }
-    if (active) {
-      const int scale = item_scale(item);
-      const uint8_t* m = nullptr;
-      if (item.pp->scaling_enabled && !tskip) {
-        const ScalingSet* sc = A.scaling + item.pp->scaling_set;
-        m = N == 8 ? sc->f8[item.cidx] : N == 16 ? sc->f16[item.cidx] : sc->f32[item.cidx];
-      }
-      constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
-#pragma unroll
-      for (int j = 0; j < N; j++) {
-        if (j < nz1) {  // warp-uniform
-          const int lvl = x[j];
-          const int ms = (m ? (int)m[j * N + col] : 16) * scale;  // <= 255 * (72 << 8) < 2^23
-          int v;
-          if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: the product fits 32 bits (the common case by far)
-            v = (lvl * ms + (1 << (BD_SHIFT - 1))) >> BD_SHIFT;
-          } else {
-            long long p = (long long)lvl * ms + (1ll << (BD_SHIFT - 1));
-            p >>= BD_SHIFT;
-            v = (int)min(32767ll, max(-32768ll, p));
-          }
-          x[j] = min(32767, max(-32768, v));
+        for (int j = 0; j < N; j++) {
+          x[j] = active ? (int)blk[j * N + col] : 0;
+          nz_rows = x[j] ? j + 1 : nz_rows;
         }
+        // extents of the non-zero coefficients, uniform over the warp so the butterfly variant is too
+        int nz1 = nz_rows;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nz1 = max(nz1, __shfl_xor_sync(0xffffffffu, nz1, o));
+        const uint32_t col_mask = __ballot_sync(0xffffffffu, nz_rows > 0);
+        // highest non-zero column index + 1 within any block of the step
+#pragma unroll
+        for (int g = 0; g < K; g++) {
+          uint32_t mg = (col_mask >> (g * N)) & (N == 32 ? 0xffffffffu : ((1u << N) - 1u));
+          nz2 = max(nz2, 32 - __clz(mg));
+        }
+        if (active) {
+          const int scale = item_scale(item);
+          const uint8_t* m = nullptr;
+          if (item.pp->scaling_enabled && !tskip) {
+            const ScalingSet* sc = A.scaling + item.pp->scaling_set;
+            m = N == 8 ? sc->f8[item.cidx] : N == 16 ? sc->f16[item.cidx] : sc->f32[item.cidx];
+          }
+          constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
+#pragma unroll
+          for (int j = 0; j < N; j++) {
+            if (j < nz1) {  // warp-uniform
+              const int lvl = x[j];
+              const int ms = (m ? (int)m[j * N + col] : 16) * scale;  // <= 255 * (72 << 8) < 2^23
+              int v;
+              if ((unsigned)(lvl + 255) <= 510u) {  // |level| <= 255: the product fits 32 bits (the common case by far)
+                v = (lvl * ms + (1 << (BD_SHIFT - 1))) >> BD_SHIFT;
+              } else {
+                long long p = (long long)lvl * ms + (1ll << (BD_SHIFT - 1));
+                p >>= BD_SHIFT;
+                v = (int)min(32767ll, max(-32768ll, p));
+              }
+              x[j] = min(32767, max(-32768, v));
+            }
+          }
+        }
+        nz = nz1;
+      } else {
+        // ---- second (row) pass: lane `col` now owns row `col` of its block ---------------------------
+        const int16_t* row = t + col * S;
+#pragma unroll
+        for (int j = 0; j < N; j += 2) {
+          uint32_t two = *reinterpret_cast<const uint32_t*>(row + j);
+          x[j] = (int)(int16_t)(two & 0xffffu);
+          x[j + 1] = (int)(int16_t)(two >> 16);
+        }
+        nz = nz2;
       }
-    }
-    if (tskip) {
+      if (tskip) {
 #pragma unroll
-      for (int i = 0; i < N; i++) y[i] = x[i];  // passed through; the rotation happens in the second pass
-    } else {
-      transform_1d<N, false>(x, y, nz1);
+        for (int i = 0; i < N; i++) y[i] = pass ? ((x[i] << 7) + 2048) >> 12 : x[i];  // rotation in the second pass
+      } else {
+        transform_1d<N, false>(x, y, nz);
+        const int add = pass ? 2048 : 64, sh = pass ? 12 : 7;
 #pragma unroll
-      for (int i = 0; i < N; i++) y[i] = clip16((y[i] + 64) >> 7);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < N; i++) t[i * S + col] = (int16_t)y[i];
-    __syncwarp();
-    // ---- second (row) pass: lane `col` now owns row `col` of its block -----------------------------
-    {
-      const int16_t* row = t + col * S;
-#pragma unroll
-      for (int j = 0; j < N; j += 2) {
-        uint32_t two = *reinterpret_cast<const uint32_t*>(row + j);
-        x[j] = (int)(int16_t)(two & 0xffffu);
-        x[j + 1] = (int)(int16_t)(two >> 16);
+        for (int i = 0; i < N; i++) y[i] = clip16((y[i] + add) >> sh);
       }
-    }
-    if (tskip) {
+      __syncwarp();
+      if (pass == 0) {
 #pragma unroll
-      for (int i = 0; i < N; i++) y[i] = ((x[i] << 7) + 2048) >> 12;
-    } else {
-      transform_1d<N, false>(x, y, nz2);
+        for (int i = 0; i < N; i++) t[i * S + col] = (int16_t)y[i];
+      } else {
+        int16_t* row = t + col * S;
 #pragma unroll
-      for (int i = 0; i < N; i++) y[i] = clip16((y[i] + 2048) >> 12);
+        for (int j = 0; j < N; j += 2)
+          *reinterpret_cast<uint32_t*>(row + j) = ((uint32_t)y[j] & 0xffffu) | ((uint32_t)y[j + 1] << 16);
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    {
-      int16_t* row = t + col * S;
-#pragma unroll
-      for (int j = 0; j < N; j += 2)
-        *reinterpret_cast<uint32_t*>(row + j) = ((uint32_t)y[j] & 0xffffu) | ((uint32_t)y[j + 1] << 16);
-    }
-    __syncwarp();
     // ---- coalesced store of the residual blocks (pairs of int16) ----------------------------------
     {
       constexpr int PAIRS = N * N / 2;  // per block
