@@ -20,12 +20,15 @@ def fuzz_bin():
 def test_mutated_files_are_rejected_or_parsed_without_memory_errors(fuzz_bin, seed0):
     r = subprocess.run([fuzz_bin, FIXTURE, str(seed0), "1000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
-    last = r.stdout.strip().splitlines()[-1]
-    assert last.startswith("done ok=")
-    ok, err = (int(x.split("=")[1]) for x in last.split()[1:])
-    assert ok + err == 1000 and ok > 0 and err > 0  # both outcomes occur: the mutations reach the parsers
+    lines = r.stdout.strip().splitlines()
+    assert lines[-1].startswith("done ok=") and lines[-2].startswith("parsers ok=")
+    ok, err = (int(x.split("=")[1]) for x in lines[-1].split()[1:])     # mutated files through the file API
+    pok, perr = (int(x.split("=")[1]) for x in lines[-2].split()[1:])   # mutated SPS / PPS / slice headers, parsed directly
+    # both outcomes occur: the mutations reach the parsers
+    assert ok + err == 1000 and ok > 0 and err > 0
+    assert pok + perr >= 3000 and pok > 0 and perr > 0
 
 
 def test_unmutated_file_parses(fuzz_bin):
     r = subprocess.run([fuzz_bin, FIXTURE, "0", "0"], capture_output=True, text=True, timeout=60)
-    assert r.returncode == 0 and r.stdout.strip().endswith("done ok=0 err=0")
+    assert r.returncode == 0 and r.stdout.strip().endswith("done ok=0 err=0")  # exits 2 if the fixture did not parse
