@@ -12,8 +12,13 @@ FIXTURE = os.path.join(HERE, "golden", "halfmoonbay.heic")
 
 @pytest.fixture(scope="module")
 def fuzz_bin():
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "fuzz")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "fuzz"), "all"])
     return os.path.join(HERE, "fuzz", "_build", "host_fuzz")
+
+
+@pytest.fixture(scope="module")
+def parser_fuzz_bin(fuzz_bin):
+    return os.path.join(HERE, "fuzz", "_build", "parser_fuzz")
 
 
 @pytest.mark.parametrize("seed0", [0, 100000])
@@ -32,3 +37,16 @@ def test_mutated_files_are_rejected_or_parsed_without_memory_errors(fuzz_bin, se
 def test_unmutated_file_parses(fuzz_bin):
     r = subprocess.run([fuzz_bin, FIXTURE, "0", "0"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0 and r.stdout.strip().endswith("done ok=0 err=0")  # exits 2 if the fixture did not parse
+
+
+@pytest.mark.parametrize("seed0", [0, 500000])
+def test_device_slice_data_parser_on_corrupt_streams_has_no_memory_errors(parser_fuzz_bin, seed0):
+    """The CUDA syntax walker (cabac_parse.cuh) in its host build, exact-size heap arenas, under ASan + UBSan: bit flips,
+    garbage, truncation, all-ones / all-zeros, moved entry points, extreme slice QPs and coding tools switched on that
+    the stream was not coded with.  compute-sanitizer is not available on the GPU pool; this is its stand-in."""
+    r = subprocess.run([parser_fuzz_bin, FIXTURE, str(seed0), "800"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
+    last = r.stdout.strip().splitlines()[-1]
+    ok, flagged = (int(x.split("=")[1]) for x in last.split()[1:])
+    assert ok + flagged == 800 and ok >= 1 and flagged > 700  # the unmutated first stream parses; corruption is detected
