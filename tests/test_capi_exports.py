@@ -62,3 +62,14 @@ def test_no_device_is_an_error_code_not_a_fallback(built):
     with pytest.raises(H.HeicError) as e:
         H.HeicDecoder()
     assert e.value.code == H._capi.HEIC_E_NO_DEVICE
+
+
+def test_rust_sys_crate_declares_every_header_entry_point():
+    """rust/heic-b200-sys is source only (no Rust toolchain here), so at least its extern block must name exactly the
+    functions include/heic_b200.h declares."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "heic_b200.h")).read()
+    rust = open(os.path.join(root, "rust", "heic-b200-sys", "src", "lib.rs")).read()
+    in_header = set(re.findall(r"\b(heic_b200_[a-z_0-9]+)\s*\(", header))
+    in_rust = set(re.findall(r"\bfn (heic_b200_[a-z_0-9]+)", rust))
+    assert in_header == in_rust, (sorted(in_header - in_rust), sorted(in_rust - in_header))
