@@ -13,11 +13,12 @@ from oracle import oracle_py as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# "flat" is the device's per-sub-block CTU loop (HEIC_CABAC_FLAT in cabac_parse.cuh), "nested" the recursive-descent form
-@pytest.fixture(scope="module", params=["nested", "flat"])
+# "nested" is the walker the device runs; "flat" (HEIC_CABAC_FLAT: per-sub-block CTU loop) and "fsm" (HEIC_CABAC_FSM: one
+# context-coded bin per iteration inside a residual block) are the opt-in experiments of cabac_parse.cuh
+@pytest.fixture(scope="module", params=["nested", "flat", "fsm"])
 def emul(request):
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emul")])
-    name = "libcabac_emul.so" if request.param == "nested" else "libcabac_emul_flat.so"
+    name = {"nested": "libcabac_emul.so", "flat": "libcabac_emul_flat.so", "fsm": "libcabac_emul_fsm.so"}[request.param]
     lib = C.CDLL(os.path.join(HERE, "emul", "_build", name))
     lib.emul_parse_picture.argtypes = ([C.POINTER(K.Sps), C.POINTER(K.Pps), C.POINTER(K.SliceHeader), C.c_void_p, C.c_uint32]
                                        + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)] * 2 + [C.c_int])
@@ -64,3 +65,36 @@ def test_device_parser_rejects_garbage_without_hanging(emul, heic_file):
                                  lv[0].ctypes.data, lv[1].ctypes.data, lv[2].ctypes.data, qp.ctypes.data, sao.ctypes.data,
                                  C.byref(bins), C.byref(ctus), 1)
     assert rc != 0  # end_of_slice / end_of_subset checks trip; no out-of-bounds write, no hang
+
+
+def _synth_cases():
+    from tests.synth.configs import CONFIGS, SEEDS
+
+    return [(name, cfg, SEEDS[0]) for name, cfg in CONFIGS]
+
+
+@pytest.mark.parametrize("name,cfg,seed", _synth_cases(), ids=[c[0] for c in _synth_cases()])
+def test_device_parser_matches_oracle_on_synthetic_streams(emul, name, cfg, seed):
+    """Every feature configuration of the synthetic generator (CTB 16/64, no WPP, transform skip, sign data hiding,
+    cu_qp_delta, transform hierarchy, 4:0:0, ragged sizes, ...) through the host build of the device parser."""
+    from tests.synth import synth
+
+    pic = synth.encode(seed, **cfg)
+    t = pic.tile
+    ref = O.decode_picture(pic.sps, pic.pps, t.header, (t.rbsp, t.rbsp_len), parse_only=True)
+    n_tu = len(ref["tu_map"])
+    tu = np.zeros(n_tu, np.uint32)
+    lv = [np.zeros(n_tu * 16, np.int16), np.zeros(n_tu * 4, np.int16), np.zeros(n_tu * 4, np.int16)]
+    qp = np.zeros(ref["qp_map"].shape, np.uint8)
+    sao = np.zeros(ref["sao"].size, np.uint32)
+    for per_row_threads in (0, 1):
+        bins, ctus = C.c_uint32(), C.c_uint32()
+        rc = emul.emul_parse_picture(C.byref(pic.sps), C.byref(pic.pps), C.byref(t.header), t.rbsp, t.rbsp_len, tu.ctypes.data,
+                                     lv[0].ctypes.data, lv[1].ctypes.data, lv[2].ctypes.data, qp.ctypes.data, sao.ctypes.data,
+                                     C.byref(bins), C.byref(ctus), per_row_threads)
+        assert rc == 0
+        assert np.array_equal(tu, ref["tu_map"])
+        for c in range(len(ref["level"])):
+            assert np.array_equal(lv[c][: ref["level"][c].size], ref["level"][c]), (name, c)
+        assert np.array_equal(qp, ref["qp_map"]) and np.array_equal(sao, ref["sao"].ravel())
+        assert (bins.value, ctus.value) == (ref["bins"], ref["ctus"])
