@@ -769,9 +769,10 @@ HEIC_NO_UNROLL
   // EXPERIMENT, off by default (-DHEIC_CABAC_FSM; bit-exact in the host emulation and on the GPU).  Measured on B200 in
   // this form it LOSES: 77.0 vs 60.3 ms per 592 images converged and 465 vs 237 ms with 32 different tiles per warp,
   // because with 32 different pictures some lane is in the bypass phase (P_LEVELS) and some lane sets up a sub-block
-  // (P_NEXT) in almost every iteration, so those two heavy bodies run once per BIN for the whole warp.  For the idea to
-  // pay, the heavy phases have to be batched: a lane that reaches one waits (skips its turns) until a ballot shows
-  // enough lanes waiting for the same phase, or no lane left that can decode a bin (next round).  The
+  // (P_NEXT) in almost every iteration, so those two heavy bodies run once per BIN for the whole warp.  Batching them
+  // (a lane that reaches one sits out until a warp ballot shows fewer than half of the unfinished lanes still decoding
+  // bins, all lanes staying in the loop until the last one is done) was measured too: 98.9 / 450 ms, no better — the
+  // loss that remains is between lanes whose transform blocks differ in size, outside this loop.  The
   // sub-blocks of one residual block decoded by a state machine whose iteration is ONE context-coded bin — the phase
   // (coded_sub_block_flag, a sig_coeff_flag, the DC flag, a greater1 flag, the greater2 flag) only chooses the context
   // before the decision and the bookkeeping after it, and the bypass-coded rest of a sub-block (signs, remaining levels,
