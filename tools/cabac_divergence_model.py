@@ -8,6 +8,12 @@ once as it is and once with one level "flattened" (the lanes' iterations of that
 first, maximum afterwards).  The ratios say which level is worth attacking; absolute numbers are a model.
 
     python tools/cabac_divergence_model.py [tiles_per_warp=32]
+    python tools/cabac_divergence_model.py sweep      # model of bench.py's k = 1..32 different tiles per warp
+
+Calibration against the B200 (CABAC stage, 592 images, before the bypass change): measured 62 / 87 / 123 / 179 / 226 /
+255 ms for k = 1 / 2 / 4 / 8 / 16 / 32; the model's ratios 1 / 1.70 / 2.69 / 3.83 / 5.12 / 6.43 fit them as
+26.5 ms + 35.5 ms x ratio (within 10 %), i.e. about 40 % of the converged time does not scale with divergence.  For the
+position-paired coding-unit loop the model gives 5.37 -> 217 ms; measured 218 ms.
 """
 import os
 import sys
@@ -160,7 +166,32 @@ def joint_by_position(nodes, positions, flat_level):
     return total
 
 
+def sweep():
+    f = H.HeicFile(open(os.path.join(ROOT, "tests", "golden", "halfmoonbay.heic"), "rb").read())
+    img = f.primary
+    order = sorted(range(img.n_tiles), key=lambda t: -img.tiles[t].rbsp_len)
+    S, P = {}, {}
+    for t in order:
+        S[t], P[t] = tile_structure(img, t)
+    n_ctu = len(S[order[0]])
+    uniform = sum(sum(lane_total(S[t][c], 0) for c in range(n_ctu)) for t in order)  # one warp step per tile
+    for by_pos in (False, True):
+        for k in (1, 2, 4, 8, 16, 32):
+            m = 0.0
+            for b0 in range(0, img.n_tiles, k):
+                lanes = order[b0:b0 + k]
+                if by_pos:
+                    j = sum(joint_by_position([S[t][c] for t in lanes], [P[t][c] for t in lanes], -1) for c in range(n_ctu))
+                else:
+                    j = sum(joint([S[t][c] for t in lanes], 0, -1) for c in range(n_ctu))
+                m += j * len(lanes)
+            print(f"{'by position' if by_pos else 'by index   '}  k = {k:2d}: {m / uniform:5.2f} x the converged cost"
+                  f"  -> {26.5 + 35.5 * m / uniform:6.1f} ms with the B200 fit")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        return sweep()
     k = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     f = H.HeicFile(open(os.path.join(ROOT, "tests", "golden", "halfmoonbay.heic"), "rb").read())
     img = f.primary
