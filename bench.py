@@ -4,11 +4,13 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                      (CPU arm: the oracle port on all host cores)
 
-A step = one decode of one resident batch of --batch images per GPU (48 tiles of 512x512 each; the images are
-seeded permutations of the 48 real tiles of halfmoonbay.heic, so every image has iPhone bit-rates while tiles
-land on different lanes/SMs).  `value` times K steps with the batch already in HBM (CUDA events on the library's
-stream); `e2e` times the reference-facing C-ABI call heic_b200_decode_grids with HOST descriptors/bitstreams in
-and pinned HOST RGB out.  Work shards by image across ranks with no data-path collective (weak scaling).
+Workload = SURVEY section 8(d) config 5: images composed by rng(seed=1) from a pool of 48 real tiles (halfmoonbay.heic)
++ 512 synthetic 512x512 WPP tiles (tests/synth: the in-repo CABAC encoder, under the fixture's own SPS/PPS), sharded
+image_idx % n_gpus (heif_b200/sharding.py).  A step = one decode of one resident batch of --batch images per GPU.  `value`
+times K steps with the batch already in HBM (CUDA events on the library's stream); `e2e` times the reference-facing C-ABI
+call heic_b200_decode_grids_submit/_job_wait with HOST descriptors/bitstreams in and pinned HOST RGB out.  No data-path
+collective (weak scaling).  The run FAILS on a wrong pixel: after warm-up, random images of the resident batch and of the
+e2e output are compared with the CPU oracle, and every 32-lane CABAC group is checked to hold 32 different tiles.
 """
 from __future__ import annotations
 
@@ -29,7 +31,10 @@ sys.path.insert(0, ROOT)
 FIXTURE = os.path.join(ROOT, "tests", "golden", "halfmoonbay.heic")
 OUT_W, OUT_H = 4032, 3024
 MP_PER_IMAGE = OUT_W * OUT_H / 1e6
-CODED_SAMPLES_PER_IMAGE = 48 * 512 * 512 * 3 // 2
+TILE_W = TILE_H = 512
+TILE_BYTES = TILE_W * TILE_H * 3 // 2
+CODED_SAMPLES_PER_IMAGE = 48 * TILE_BYTES
+SEED = 1
 
 
 def peaks():
@@ -38,26 +43,6 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def make_images(heic_file, n_images: int, seed: int):
-    """n_images descriptors whose tiles are seeded permutations of the fixture's 48 tiles."""
-    from heif_b200 import _capi as K
-
-    base = heic_file.primary
-    rng = np.random.default_rng(seed)
-    keep, images = [], []
-    for _ in range(n_images):
-        perm = rng.permutation(base.n_tiles)
-        tiles = (K.TileDesc * base.n_tiles)()
-        for d, s in enumerate(perm):
-            C.memmove(C.byref(tiles, d * C.sizeof(K.TileDesc)), C.byref(base.tiles[int(s)]), C.sizeof(K.TileDesc))
-        im = K.ImageDesc()
-        C.memmove(C.byref(im), C.byref(base), C.sizeof(K.ImageDesc))
-        im.tiles = C.cast(tiles, C.POINTER(K.TileDesc))
-        keep.append(tiles)
-        images.append(im)
-    return images, keep
 
 
 class ClockSampler:
@@ -97,10 +82,6 @@ class ClockSampler:
             return None
 
 
-# ---------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (oracle/hevc_oracle.c) on the host cores.  kind = "port": the reference is Rust,
-# there is no cargo/rustc in the image, and its slice decoder ends in todo!() anyway ("Oracle").
-# ---------------------------------------------------------------------------------------------------------
 def host_memory_available() -> int:
     """Bytes of host memory this process may still use: MemAvailable, capped by the cgroup limit if there is one."""
     avail = 64 << 30
@@ -148,36 +129,50 @@ def bind_to_gpu_numa_node(index: int) -> str:
         return f"not bound ({type(e).__name__}: {e})"
 
 
-def cpu_decode_images(heic_file, n_images: int, threads: int) -> float:
-    """Decodes n_images x 48 tiles + colour/stitch with `threads` host threads; returns seconds."""
-    from concurrent.futures import ThreadPoolExecutor
+# ---------------------------------------------------------------------------------------------------------
+# CPU side: the oracle port (oracle/hevc_oracle.c) on the host cores.  kind = "port": the reference is Rust, there is no
+# cargo/rustc in the image, and its slice decoder ends in todo!() anyway ("Oracle").  It serves twice: as the
+# checker of the GPU pixels and as the timed CPU baseline / reference arm.
+# ---------------------------------------------------------------------------------------------------------
+class CpuDecoder:
+    """Decodes images of the job with the oracle.  All buffers are allocated up front; the timed part is C calls only
+    (hevc_oracle_decode_picture per tile, hevc_oracle_color_stitch per grid row), spread over `threads` host threads."""
 
-    from oracle import oracle_py
+    def __init__(self, pool, base_image, threads: int):
+        from concurrent.futures import ThreadPoolExecutor
 
-    img = heic_file.primary
-    w, h = img.sps.pic_width_in_luma_samples, img.sps.pic_height_in_luma_samples
+        from oracle import oracle_py
 
-    def one(t):
-        td = img.tiles[t % img.n_tiles]
-        r = oracle_py.decode_picture(img.sps, img.pps, td.header, (td.rbsp, td.rbsp_len), intermediates=False)
-        return np.concatenate([p.ravel() for p in r["plane"]])
+        oracle_py.load()
+        self.O = oracle_py
+        self.pool, self.img, self.threads = pool, base_image, threads
+        self.ex = ThreadPoolExecutor(threads)
 
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(threads) as ex:
-        planes = list(ex.map(one, range(n_images * img.n_tiles)))
-        # colour + stitch one grid row per task (the last row is cropped by the canvas height)
-        jobs = []
-        for i in range(n_images):
-            for r in range(img.grid_rows):
-                row = np.concatenate(planes[i * img.n_tiles + r * img.grid_cols:i * img.n_tiles + (r + 1) * img.grid_cols])
-                jobs.append((row, min(h, img.output_height - r * h)))
-        list(ex.map(lambda j: oracle_py.color_stitch(j[0], 1, img.grid_cols, w, h, img.output_width, j[1],
-                                                     img.sps.video_full_range_flag, img.sps.matrix_coeffs), jobs))
-    return time.perf_counter() - t0
+    def decode(self, ids: np.ndarray, planes: np.ndarray, rgb: np.ndarray) -> float:
+        """ids [n, 48] pool entries -> planes [n, 48, TILE_BYTES], rgb [n, OUT_H, OUT_W, 3]; returns seconds."""
+        O, pool, img = self.O, self.pool, self.img
+        n, nt = ids.shape
+        cols, rows = img.grid_cols, img.grid_rows
+        fr, mc = img.sps.video_full_range_flag, img.sps.matrix_coeffs
+
+        def tile(k):
+            i, t = divmod(k, nt)
+            td = pool.descs[int(ids[i, t])]
+            O.decode_picture_into(pool.sps, pool.pps, td.header, td.rbsp, td.rbsp_len, planes[i, t])
+
+        def row(k):  # colour + stitch of one grid row (the last row is cropped by the canvas height)
+            i, r = divmod(k, rows)
+            O.color_stitch_into(planes[i, r * cols].ctypes.data, 1, cols, TILE_W, TILE_H, OUT_W, min(TILE_H, OUT_H - r * TILE_H),
+                                fr, mc, rgb[i, r * TILE_H].ctypes.data, OUT_W * 3)
+
+        t0 = time.perf_counter()
+        list(self.ex.map(tile, range(n * nt)))
+        list(self.ex.map(row, range(n * rows)))
+        return time.perf_counter() - t0
 
 
 def ffmpeg_decode_images(heic_file, n_images: int, threads: int):
-    """FFmpeg's native HEVC decoder (planes only, no colour conversion) on the same tiles, one decoder per thread.
+    """FFmpeg's native HEVC decoder (planes only, no colour conversion) on the fixture's real tiles, one decoder per thread.
     Extra context next to the oracle port: 'what a CPU does today'.  Returns seconds, or None when FFmpeg is absent."""
     try:
         from concurrent.futures import ThreadPoolExecutor
@@ -205,37 +200,67 @@ def ffmpeg_decode_images(heic_file, n_images: int, threads: int):
 
 
 # the workload both arms name in `config` (BASELINE.json configs[4], image-sharded)
-WORKLOAD = "configs[4] sharded: 12 MP 8x6 grid of 512x512 HEVC intra tiles (WPP, SAO, deblock, scaling lists) -> RGB 4032x3024"
+WORKLOAD = ("configs[4] sharded: 12 MP 8x6 grid images of 512x512 HEVC intra tiles (WPP, SAO, deblock, scaling lists) -> RGB 4032x3024; "
+            "tiles drawn by rng(seed=1) from a pool of 48 real + 512 synthetic tiles (SURVEY 8(d) config 5)")
+
+
+def data_note(pool):
+    c = pool.composition()
+    return (f"pool of {c['real_tiles']} real tiles (halfmoonbay.heic) + {c['synthetic_tiles']} synthetic 512x512 WPP tiles (in-repo CABAC "
+            f"encoder, QP / lps_gain sweep; slice bytes min/quartiles/max real {c['slice_bytes_quartiles_real']}, synthetic "
+            f"{c['slice_bytes_quartiles_synthetic']}); every image = 48 distinct pool tiles by rng(seed={SEED}, image_idx)")
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import heif_b200
-    from oracle import oracle_py
+    # The CPU arm reads its inputs through a host-only build of the repo's parse layer (oracle/_build/libheic_host.so):
+    # the product library libheic_b200.so is never mapped into this process.
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+    from heif_b200 import _capi
 
-    oracle_py.load()
+    _capi.load(os.path.join(ROOT, "oracle", "_build", "libheic_host.so"), host_only=True)
+    import heif_b200
+    from tests.synth import pool as P
+
     f = heif_b200.HeicFile(open(FIXTURE, "rb").read())
     cores = os.cpu_count() or 1
+    pool = P.build_pool(f, args.pool)
     n_img = max(1, args.ref_images)
+    ids = np.stack([P.image_tile_ids(len(pool), i, f.primary.n_tiles, SEED) for i in range(n_img)])
+    cpu = CpuDecoder(pool, f.primary, cores)
+    planes = np.zeros((n_img, 48, TILE_BYTES), np.uint8)
+    rgb = np.zeros((n_img, OUT_H, OUT_W, 3), np.uint8)
     for _ in range(args.warmup):
-        cpu_decode_images(f, n_img, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_decode_images(f, n_img, cores)
-    dt = time.perf_counter() - t0
+        cpu.decode(ids, planes, rgb)
+    dt = sum(cpu.decode(ids, planes, rgb) for _ in range(args.steps))
     value = args.steps * n_img * MP_PER_IMAGE / dt
-    sample = f"{n_img} image(s) = {48 * n_img} real 512x512 tiles of halfmoonbay.heic per step, oracle port (C, -O3), {cores} threads"
+    sample = f"images 0..{n_img - 1} of the job = {48 * n_img} tiles per step, oracle port (C, -O3), {cores} threads"
     print(json.dumps({
         "impl": "reference", "metric": "decoded MP/s (12MP HEIC grid batch)", "value": round(value, 3), "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "halfmoonbay.heic tiles (real), CPU",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": data_note(pool) + ", CPU",
         "config": {"workload": WORKLOAD, "images_per_step": n_img, "note": "bounded CPU sample of the same workload"},
         "cpu_baseline": {"value": round(value, 3), "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
+
+
+def check_groups_distinct(batch, ids_flat: np.ndarray) -> dict:
+    """Every CABAC warp-group must hold different pool tiles (copies of one tile in a warp would run converged)."""
+    order, tpg = batch.cabac_order()
+    if tpg != 32:
+        return {"tiles_per_group": tpg}
+    g = order.reshape(-1, 32)
+    valid = g != 0xFFFFFFFF
+    pid = np.where(valid, ids_flat[np.where(valid, g, 0)], -1 - np.arange(32)[None, :])  # idle lanes: unique dummies
+    s = np.sort(pid, axis=1)
+    dup = int((s[:, 1:] == s[:, :-1]).any(axis=1).sum())
+    if dup:
+        raise SystemExit(f"{dup} CABAC groups hold two copies of one tile: the batch would measure converged warps")
+    return {"tiles_per_group": 32, "groups": int(g.shape[0]), "lane_fill": round(float(valid.mean()), 4), "groups_with_duplicates": 0}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -246,11 +271,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=int(os.environ.get("HEIC_BENCH_BATCH", "592")), help="images per GPU per step")
+    ap.add_argument("--pool", type=int, default=512, help="synthetic tiles in the pool (beside the 48 real ones)")
     ap.add_argument("--e2e-batch", type=int, default=int(os.environ.get("HEIC_BENCH_E2E_BATCH", "256")), help="images per reference-facing call")
     ap.add_argument("--ref-images", type=int, default=64, help="images per step of the CPU arm")
-    ap.add_argument("--cpu-images", type=int, default=256, help="images in the cpu_baseline sample")
+    ap.add_argument("--cpu-images", type=int, default=128, help="images in the cpu_baseline sample")
+    ap.add_argument("--check-images", type=int, default=8, help="images compared pixel by pixel with the oracle")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-mixed", action="store_true", help="skip the mixed-warp measurement (32 different tiles per CABAC warp)")
+    ap.add_argument("--no-converged", action="store_true", help="skip the copies-of-one-tile-per-warp upper bound")
     ap.add_argument("--stages", action="store_true", help="also print a per-stage table to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -259,6 +286,8 @@ def main():
     import torch
 
     import heif_b200 as H
+    from heif_b200 import sharding
+    from tests.synth import pool as P
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,15 +311,20 @@ def main():
 
     f = H.HeicFile(open(FIXTURE, "rb").read())
     dec = H.HeicDecoder(device=local)
-    images, keep = make_images(f, args.batch, seed=1 + rank)
+    pool = P.build_pool(f, args.pool, threads=max(2, (os.cpu_count() or 2) // world))
+    # the job: world * batch images, image i on rank i % world
+    n_job = world * args.batch
+    my_images = list(sharding.shard_modulo(n_job, rank, world))
+    images, keep, ids = P.compose_images(pool, f.primary, my_images, SEED)
     batch = dec.batch(images)
+    groups = check_groups_distinct(batch, ids.reshape(-1))
     stream = torch.cuda.ExternalStream(batch.stream, device=torch.device("cuda", local))
     hbm_peak, peak_src = peaks()
 
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
-    # ---- value: K steps, batch resident in HBM -----------------------------------------------------------
+    # ---- warm-up, then the pixel check: random images of the resident batch against the CPU oracle ------------------
     for _ in range(max(args.warmup, 3)):
         batch.decode()
     batch.sync()
@@ -299,6 +333,23 @@ def main():
     if bad:
         raise SystemExit(f"{len(bad)} tiles failed to decode")
     bins_per_step = sum(st[i].bins_decoded for i in range(batch.n_tiles))
+    n_chk = min(args.check_images, args.batch)
+    cpu_threads = max(1, (os.cpu_count() or 1) // world)
+    cpu_dec = CpuDecoder(pool, f.primary, cpu_threads)
+    chk = np.sort(np.random.default_rng(1234 + rank).choice(args.batch, size=n_chk, replace=False))
+    eb = min(args.e2e_batch, args.batch)
+    chk[0] = min(int(chk[0]), eb - 1)  # at least one of them also lies inside the e2e call
+    chk = np.unique(chk)
+    ref_planes = np.zeros((len(chk), 48, TILE_BYTES), np.uint8)
+    ref_rgb = np.zeros((len(chk), OUT_H, OUT_W, 3), np.uint8)
+    cpu_dec.decode(ids[chk], ref_planes, ref_rgb)
+    for k, i in enumerate(chk):
+        got = batch.download_image(int(i))
+        if not np.array_equal(got, ref_rgb[k]):
+            raise SystemExit(f"resident batch, image {int(i)}: {int((got != ref_rgb[k]).sum())} RGB bytes differ from the oracle")
+    pixel_check = {"resident_images_checked": [int(i) for i in chk], "vs": "CPU oracle (decode + the frozen colour definition), bit-exact"}
+
+    # ---- value: K steps, batch resident in HBM -----------------------------------------------------------
     barrier()
     clocks = ClockSampler(local) if rank == 0 else None
     l0 = dec.launch_count()
@@ -339,30 +390,37 @@ def main():
     batch.sync()
     fused_ms = fe[0].elapsed_time(fe[reps]) / reps
 
-    # coded samples (cbf = 1) for the algorithmic bytes of the transform / intra stages
-    tu = [batch.dump_tile(t)["tu_map"] for t in range(48)]
-    coded = 0
-    for m in tu:
+    # coded samples (cbf = 1) per pool tile, for the algorithmic bytes of the transform / intra stages: measured on the
+    # first tile of every pool entry that occurs in this rank's batch
+    flat = ids.reshape(-1)
+    first_of = {}
+    for t, pid in enumerate(flat):
+        first_of.setdefault(int(pid), t)
+    coded_of = {}
+    for pid, t in first_of.items():
+        m = batch.dump_tile(t)["tu_map"]
         o = m[(m & 1) == 1]
         n2 = (4 << ((o >> 1) & 3)).astype(np.int64) ** 2
-        coded += int((n2 * ((o >> 3) & 1)).sum())
+        c = int((n2 * ((o >> 3) & 1)).sum())
         nc = np.where(((o >> 1) & 3) == 0, 16, n2 // 4)
-        coded += int((nc * ((o >> 6) & 1) * (((o >> 4) & 1) + ((o >> 5) & 1))).sum())
-    coded_per_image = coded  # every image is a permutation of the same 48 tiles
+        c += int((nc * ((o >> 6) & 1) * (((o >> 4) & 1) + ((o >> 5) & 1))).sum())
+        coded_of[pid] = c
     n_img = args.batch
+    coded_total = int(sum(coded_of[int(pid)] for pid in flat))
+    slice_bytes_total = int(sum(pool.descs[int(pid)].rbsp_len for pid in flat))
     a_c = CODED_SAMPLES_PER_IMAGE
-    alg_bytes = {  # per image, SURVEY.md section 8(d)
-        "cabac": 1704187 + 2 * coded_per_image,          # slice data in + TransCoeffLevel out (dense int16 of coded blocks)
-        "transform": 4 * coded_per_image,                 # 2 B in + 2 B out per coded sample
-        "intra": 2 * coded_per_image + a_c,               # residual in + reconstructed planes out
-        "deblock": 2 * a_c,                               # planes in + out
-        "sao": 2 * a_c,
-        "color_stitch": int(4.5 * OUT_W * OUT_H),         # 1.5 B in + 3 B out per output pixel
+    alg_bytes = {  # per step (whole batch), SURVEY.md section 8(d)
+        "cabac": slice_bytes_total + 2 * coded_total,        # slice data in + TransCoeffLevel out (dense int16 of coded blocks)
+        "transform": 4 * coded_total,                        # 2 B in + 2 B out per coded sample
+        "intra": 2 * coded_total + a_c * n_img,              # residual in + reconstructed planes out
+        "deblock": 2 * a_c * n_img,                          # planes in + out
+        "sao": 2 * a_c * n_img,
+        "color_stitch": int(4.5 * OUT_W * OUT_H) * n_img,    # 1.5 B in + 3 B out per output pixel
     }
     stages = []
     for n, _ in stage_defs:
-        gbs = alg_bytes[n] * n_img / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0
-        stages.append({"kernel": n, "ms": round(stage_ms[n], 4), "alg_GB": round(alg_bytes[n] * n_img / 1e9, 4),
+        gbs = alg_bytes[n] / (stage_ms[n] * 1e-3) / 1e9 if stage_ms[n] > 0 else 0.0
+        stages.append({"kernel": n, "ms": round(stage_ms[n], 4), "alg_GB": round(alg_bytes[n] / 1e9, 4),
                        "achieved_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / hbm_peak, 4)})
     dom = max(stages, key=lambda s: s["ms"])
     traffic = None
@@ -375,8 +433,7 @@ def main():
     cabac_bins = bins_per_step / (stage_ms["cabac"] * 1e-3)
 
     # ---- e2e: host descriptors + bitstreams in, pinned host RGB out, through heic_b200_decode_grids ----------
-    # pinned host RGB: 2 x 36.6 MB per image per rank; all ranks together may pin a quarter of the host memory that is free
-    eb = min(args.e2e_batch, args.batch)
+    # pinned host RGB: 2 x 36.6 MB per image per rank; all ranks together may pin 40 % of the host memory that is free
     if world > 1:
         fit = torch.tensor([int(0.4 * host_memory_available() / world / (2 * OUT_H * OUT_W * 3))], device="cuda", dtype=torch.int64)
         dist.all_reduce(fit, op=dist.ReduceOp.MIN)  # the same call size on every rank
@@ -390,10 +447,16 @@ def main():
     # overlap call k's device->host copy.  Every call carries all of its own copies; two pinned output buffers alternate.
     out2 = torch.empty((eb, OUT_H, OUT_W, 3), dtype=torch.uint8, pin_memory=True)
     outs = [out_np, out2.numpy()]
-    # warm-up: the library's 8 pipeline slots (32 images each) allocate their arenas on first use, so run enough calls to
-    # have touched every slot before the timed region
+    # warm-up: the library's pipeline slots allocate their arenas on first use, so run enough calls to have touched every
+    # slot before the timed region
     for k in range(max(2, -(-8 * 32 // eb) + 1)):
         dec.decode_grids(images[:eb], out=outs[k & 1])
+    for k, i in enumerate(chk):  # pixels of the reference-facing call as well
+        if i < eb:
+            for o in outs:  # the warm-up wrote both buffers
+                if not np.array_equal(o[int(i)], ref_rgb[k]):
+                    raise SystemExit(f"decode_grids, image {int(i)}: RGB differs from the oracle")
+    pixel_check["e2e_images_checked"] = [int(i) for i in chk if i < eb]
     barrier()
     e2e_steps = max(3, min(args.steps, 6))
     t0 = time.perf_counter()
@@ -417,110 +480,108 @@ def main():
     e2e_val = eb * MP_PER_IMAGE / e2e_s
 
     # ---- aggregate over ranks: max time --------------------------------------------------------------------
+    ms, sums = sharding.reduce_timing(dist, torch.device("cuda", local), ms, {"bins": float(bins_per_step)})
     if dist is not None:
-        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1])
+        e2e_s = float(t[0])
         e2e_val = eb * MP_PER_IMAGE / e2e_s
     value = world * args.steps * n_img * MP_PER_IMAGE / (ms * 1e-3)
     e2e_total = world * e2e_val
 
-    # ---- the same batch with 32 DIFFERENT tiles in every CABAC warp ----------------------------------------------
-    # The batch repeats the fixture's 48 tiles, and sorting by slice size (what the library does for any input) puts
-    # copies of one tile into the 32 lanes of a warp, which then run fully converged.  A batch of distinct photographs has
-    # no such copies; the library's measurement knob deals 32 neighbouring-size tiles into each warp to show that case.
-    mixed = None
-    if world == 1 and not args.no_mixed:
+    # ---- upper bound for context: copies of ONE tile in every CABAC warp (what a batch of 48 repeated tiles measures) ----
+    converged = None
+    if world == 1 and not args.no_converged:
         batch.close()
-        dec.close()
-        os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"] = "32", str(args.batch)
-        dec = H.HeicDecoder(device=local)
-        del os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"]
-        batch = dec.batch(images)
-        stream = torch.cuda.ExternalStream(batch.stream, device=torch.device("cuda", local))
+        rng = np.random.default_rng(SEED)
+        perm_ids = np.stack([rng.permutation(48) for _ in range(args.batch)])  # real tiles only, 592 copies of each
+        os.environ["HEIC_B200_CABAC_DEAL"] = "1"  # plain size sort: the copies of a tile land in the same warps
+        dec2 = H.HeicDecoder(device=local)
+        del os.environ["HEIC_B200_CABAC_DEAL"]
+        imgs2, keep2 = [], []
+        tsize = C.sizeof(H._capi.TileDesc)
+        for i in range(args.batch):
+            tiles = (H._capi.TileDesc * 48)()
+            for d, s in enumerate(perm_ids[i]):
+                C.memmove(C.byref(tiles, d * tsize), C.byref(pool.descs[int(s)]), tsize)
+            im = H._capi.ImageDesc()
+            C.memmove(C.byref(im), C.byref(f.primary), C.sizeof(H._capi.ImageDesc))
+            im.tiles = C.cast(tiles, C.POINTER(H._capi.TileDesc))
+            keep2.append(tiles)
+            imgs2.append(im)
+        b2 = dec2.batch(imgs2)
+        s2 = torch.cuda.ExternalStream(b2.stream, device=torch.device("cuda", local))
         for _ in range(2):
-            batch.decode()
-        batch.sync()
+            b2.decode()
+        b2.sync()
         m0, m1, m2 = ev(), ev(), ev()
-        m0.record(stream)
+        m0.record(s2)
         for _ in range(2):
-            batch.decode()
-        m1.record(stream)
-        batch.run(H.STAGE_CABAC)
-        m2.record(stream)
-        batch.sync()
-        st2 = batch.status()
-        if any(st2[i].code != 0 for i in range(batch.n_tiles)):
-            raise SystemExit("mixed-warp decode failed")
-        mixed_ms = m0.elapsed_time(m1) / 2
-        # the end-to-end loop the same way (its chunks of 32 images hold 32 copies of every tile as well)
-        batch.close()
-        dec.close()
-        os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"] = "32", os.environ.get("HEIC_B200_PIPE_CHUNK", "32")
-        dec = H.HeicDecoder(device=local)
-        del os.environ["HEIC_B200_PROBE_MIX_K"], os.environ["HEIC_B200_PROBE_MIX_P"]
-        batch = dec.batch(images[:1])
-        for _ in range(2):
-            dec.decode_grids(images[:eb], out=out_np)
-        t0 = time.perf_counter()
-        prev = None
-        for k in range(e2e_steps):
-            job = dec.submit_grids(images[:eb], outs[k & 1])
-            if prev is not None:
-                dec.wait_job(prev)
-            prev = job
-        dec.wait_job(prev)
-        torch.cuda.synchronize()
-        mixed_e2e_s = (time.perf_counter() - t0) / e2e_steps
-        mixed = {"value": round(n_img * MP_PER_IMAGE / (mixed_ms * 1e-3), 2), "unit": "MP/s", "ms_per_step": round(mixed_ms, 4),
-                 "e2e": round(eb * MP_PER_IMAGE / mixed_e2e_s, 2),
-                 "cabac_ms": round(m1.elapsed_time(m2), 4),
-                 "note": "same batch, resident, but every CABAC warp holds 32 different tiles of neighbouring size (no copies "
-                         "of one tile in a warp, as in a batch of distinct photographs; includes the size spread of the "
-                         "fixture's 48 tiles); `value` has copies of one tile in each warp"}
+            b2.decode()
+        m1.record(s2)
+        b2.run(H.STAGE_CABAC)
+        m2.record(s2)
+        b2.sync()
+        c_ms = m0.elapsed_time(m1) / 2
+        converged = {"value": round(n_img * MP_PER_IMAGE / (c_ms * 1e-3), 2), "unit": "MP/s", "ms_per_step": round(c_ms, 4),
+                     "cabac_ms": round(m1.elapsed_time(m2), 4),
+                     "note": "UPPER BOUND, not the workload: a batch that repeats the fixture's 48 real tiles, size-sorted so that "
+                             "every CABAC warp holds 32 copies of one tile and never diverges (round 1's headline)"}
+        b2.close()
+        dec2.close()
+        batch = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import oracle_py
-
-        oracle_py.load()
         cores = os.cpu_count() or 1
-        dt = cpu_decode_images(f, args.cpu_images, cores)
-        cpu = {"value": round(args.cpu_images * MP_PER_IMAGE / dt, 3), "unit": "MP/s", "cores": cores, "kind": "port",
-               "sample": f"{args.cpu_images} images = {48 * args.cpu_images} real tiles of halfmoonbay.heic, oracle port (C -O3), {cores} threads, {dt:.1f} s"}
-        fdt = ffmpeg_decode_images(f, args.cpu_images, cores)
+        n_cpu = args.cpu_images
+        cids = np.stack([P.image_tile_ids(len(pool), i, 48, SEED) for i in range(n_cpu)])
+        cpl = np.zeros((n_cpu, 48, TILE_BYTES), np.uint8)
+        crgb = np.zeros((n_cpu, OUT_H, OUT_W, 3), np.uint8)
+        dt = CpuDecoder(pool, f.primary, cores).decode(cids, cpl, crgb)
+        cpu = {"value": round(n_cpu * MP_PER_IMAGE / dt, 3), "unit": "MP/s", "cores": cores, "kind": "port",
+               "sample": f"images 0..{n_cpu - 1} of the job = {48 * n_cpu} tiles, oracle port (C -O3), {cores} threads, {dt:.1f} s"}
+        del cpl, crgb
+        fdt = ffmpeg_decode_images(f, 64, cores)
         if fdt:
-            cpu["ffmpeg_hevc"] = {"value": round(args.cpu_images * MP_PER_IMAGE / fdt, 3), "unit": "MP/s", "cores": cores,
-                                  "note": "FFmpeg native hevc decoder, YCbCr planes only (no colour conversion), same tiles; context, not the reference"}
+            cpu["ffmpeg_hevc"] = {"value": round(64 * MP_PER_IMAGE / fdt, 3), "unit": "MP/s", "cores": cores,
+                                  "note": "FFmpeg native hevc decoder, YCbCr planes only (no colour conversion), the 48 real tiles; context, not the reference"}
 
     if rank == 0:
         line = {
             "metric": "decoded MP/s (12MP HEIC grid batch)", "value": round(value, 2), "unit": "MP/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "halfmoonbay.heic's 48 real 512x512 tiles, seeded permutation per image (synthetic batch of real bitstreams; every "
-                    "tile therefore occurs once per image, see distinct_tiles_per_warp)",
+            "data": "synthetic batch: " + data_note(pool),
             "config": {"workload": WORKLOAD,
-                       "images_per_gpu_per_step": n_img, "tiles_per_step_per_gpu": n_img * 48, "parallelism": f"image-sharded x{world}, no collective",
+                       "images_per_gpu_per_step": n_img, "tiles_per_step_per_gpu": n_img * 48, "images_in_job": n_job,
+                       "parallelism": f"image_idx % {world} (heif_b200/sharding.py), no collective",
                        "l2": "working set per step >> 126 MB L2 (inputs larger than L2)",
-                       "cabac_tiles_per_cta": int(os.environ.get("HEIC_B200_CABAC_TILES_PER_CTA", "32"))},
-            "roofline": {"kernel": dom["kernel"], "bound": "hbm", "achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                         "frac": dom["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
-                         "note": "dominant kernel by time; CABAC is serial-latency bound (see cabac_bins_per_s_per_sm), per-kernel rooflines in `stages`"},
+                       "cabac_groups": groups},
+            "roofline": {"kernel": dom["kernel"], "bound": "latency" if dom["kernel"] == "cabac" else "hbm",
+                         "achieved": round(cabac_bins / n_sm / 1e9, 4) if dom["kernel"] == "cabac" else dom["achieved_GBps"],
+                         "peak": None if dom["kernel"] == "cabac" else hbm_peak,
+                         "unit": "Gbin/s/SM" if dom["kernel"] == "cabac" else "GB/s",
+                         "frac": None if dom["kernel"] == "cabac" else dom["frac_of_hbm_peak"],
+                         "hbm": {"achieved": dom["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["frac_of_hbm_peak"]},
+                         "traffic": traffic, "peak_source": peak_src,
+                         "note": "dominant kernel by time.  CABAC is bound by the serial bin chain, not by a throughput roofline: "
+                                 "`achieved` is bins/s/SM (SURVEY 8(d)); its HBM figure is under `hbm`; per-kernel rooflines in `stages`"},
             "stages": stages,
-            "fused_sao_color": {"ms": round(fused_ms, 4), "alg_GB": round(alg_bytes["color_stitch"] * n_img / 1e9, 4),
-                                "achieved_GBps": round(alg_bytes["color_stitch"] * n_img / (fused_ms * 1e-3) / 1e9, 1),
-                                "frac_of_hbm_peak": round(alg_bytes["color_stitch"] * n_img / (fused_ms * 1e-3) / 1e9 / hbm_peak, 4),
+            "fused_sao_color": {"ms": round(fused_ms, 4), "alg_GB": round(alg_bytes["color_stitch"] / 1e9, 4),
+                                "achieved_GBps": round(alg_bytes["color_stitch"] / (fused_ms * 1e-3) / 1e9, 1),
+                                "frac_of_hbm_peak": round(alg_bytes["color_stitch"] / (fused_ms * 1e-3) / 1e9 / hbm_peak, 4),
                                 "note": "a full decode applies SAO inside the colour kernel (1.5 B in + 3 B out per output pixel); "
                                         "`sao` and `color_stitch` above are the stand-alone stages"},
-            "cabac_bins_per_s_per_sm": round(cabac_bins / n_sm, 1), "cabac_bins_per_image": bins_per_step // n_img,
+            "cabac_bins_per_s_per_sm": round(cabac_bins / n_sm, 1), "cabac_bins_per_image": int(sums["bins"] / world) // n_img,
             "coded_mp_per_s": round(value * (48 * 512 * 512) / (OUT_W * OUT_H), 2),
+            "pixel_check": pixel_check,
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_total, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "images_per_call": eb, "host_affinity": affinity, "ms_per_call": round(e2e_s * 1e3, 3), "host_submit_ms_per_call": round(submit_s / e2e_steps * 1e3, 3),
                     "mode": "double-buffered heic_b200_decode_grids_submit/_job_wait, pinned host RGB",
                     "synchronous_call_MPps": round(world * eb * MP_PER_IMAGE / sync_s, 2)},
-            "distinct_tiles_per_warp": mixed,
+            "copies_per_warp_upper_bound": converged,
             "gpu_launches": int(launches),
             "clocks": clk,
         }
@@ -528,7 +589,8 @@ def main():
         if args.stages:
             for s in stages:
                 print(s, file=sys.stderr)
-    batch.close()
+    if batch is not None:
+        batch.close()
     dec.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -202,6 +202,14 @@ class Batch:
     def n_tiles(self) -> int:
         return self._lib.heic_b200_batch_tile_count(self._h)
 
+    def cabac_order(self):
+        """(tile indices in CABAC launch order with 0xffffffff for idle lanes, tiles per warp-group)."""
+        tpg = C.c_uint32()
+        n = self._lib.heic_b200_batch_cabac_order(self._h, None, 0, C.byref(tpg))
+        out = np.zeros(n, np.uint32)
+        self._lib.heic_b200_batch_cabac_order(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), n, C.byref(tpg))
+        return out, int(tpg.value)
+
     @property
     def stream(self) -> int:
         return int(self._lib.heic_b200_batch_stream(self._h) or 0)
@@ -225,6 +233,13 @@ class Batch:
         if out is None:
             out = np.empty((len(self.images), h, w, 3), np.uint8)
         K.check(self._lib.heic_b200_batch_download_rgb(self._h, out.ctypes.data, out.strides[1], out.strides[0]))
+        return out
+
+    def download_image(self, index: int) -> np.ndarray:
+        """RGB of one image of the batch (H, W, 3)."""
+        w, h = _canvas(self.images[index], False)
+        out = np.empty((h, w, 3), np.uint8)
+        K.check(self._lib.heic_b200_batch_download_image(self._h, index, out.ctypes.data, out.strides[0]))
         return out
 
     def status(self):

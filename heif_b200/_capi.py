@@ -178,8 +178,10 @@ SYMBOLS = [
     ("heic_b200_batch_stream", _vp, [_vp]),
     ("heic_b200_batch_rgb", i32, [_vp, C.POINTER(_vp), C.POINTER(_sz), C.POINTER(_sz)]),
     ("heic_b200_batch_download_rgb", i32, [_vp, _vp, _sz, _sz]),
+    ("heic_b200_batch_download_image", i32, [_vp, u32, _vp, _sz]),
     ("heic_b200_batch_status", i32, [_vp, C.POINTER(TileStatus)]),
     ("heic_b200_batch_tile_count", u32, [_vp]),
+    ("heic_b200_batch_cabac_order", _sz, [_vp, C.POINTER(u32), _sz, C.POINTER(u32)]),
     ("heic_b200_batch_dump_tile", i32, [_vp, u32, C.POINTER(TileDump)]),
     ("heic_b200_color_stitch", i32,
      [_vp, _vp, u32, u32, u32, u32, u32, u32, u32, u32, u32, _vp, _sz, _sz]),
@@ -188,8 +190,10 @@ SYMBOLS = [
 _lib = None
 
 
-def load(path: str | None = None) -> C.CDLL:
-    """dlopen the C-ABI library and bind every declared symbol.  Raises if absent (no fallback)."""
+def load(path: str | None = None, host_only: bool = False) -> C.CDLL:
+    """dlopen the C-ABI library and bind every declared symbol.  Raises if absent (no fallback).
+    host_only (bench.py's CPU arm): `path` is a build of the host parse layer alone (oracle/_build/libheic_host.so); it
+    becomes the process-wide library and only the symbols it has are bound -- every compute entry point is then absent."""
     global _lib
     if _lib is not None and path is None:
         return _lib
@@ -201,10 +205,12 @@ def load(path: str | None = None) -> C.CDLL:
         )
     lib = C.CDLL(p)
     for name, restype, argtypes in SYMBOLS:
+        if host_only and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = restype
         fn.argtypes = argtypes
-    if path is None:
+    if path is None or host_only:
         _lib = lib
     return lib
 

@@ -197,11 +197,9 @@ cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t*
   const size_t smem = cabac_smem_bytes(tiles_per_cta, n_slots) + pad;
   const int threads = 32 * n_slots;
   if (tiles_per_cta == 32) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    {  // per device, and several devices may be driven from one process: set it on every launch (cheap)
       cudaError_t e = cudaFuncSetAttribute(cabac_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       if (e != cudaSuccess) return e;
-      attr_set = true;
     }
     // persistent CTAs when there is more than one wave of groups (group ids are 20 bits in the hand-over slot)
     // HEIC_CABAC_MIN_CTAS CTAs of 8 warps are resident per SM: proportionally more when a CTA has fewer row slots

@@ -765,167 +765,10 @@ HEIC_NO_UNROLL
       num_sig++;
     }
   }
-#if defined(HEIC_CABAC_FSM)
-  // EXPERIMENT, off by default (-DHEIC_CABAC_FSM; bit-exact in the host emulation and on the GPU).  Measured on B200 in
-  // this form it LOSES: 77.0 vs 60.3 ms per 592 images converged and 465 vs 237 ms with 32 different tiles per warp,
-  // because with 32 different pictures some lane is in the bypass phase (P_LEVELS) and some lane sets up a sub-block
-  // (P_NEXT) in almost every iteration, so those two heavy bodies run once per BIN for the whole warp.  Batching them
-  // (a lane that reaches one sits out until a warp ballot shows fewer than half of the unfinished lanes still decoding
-  // bins, all lanes staying in the loop until the last one is done) was measured too: 98.9 / 450 ms, no better — the
-  // loss that remains is between lanes whose transform blocks differ in size, outside this loop.  The
-  // sub-blocks of one residual block decoded by a state machine whose iteration is ONE context-coded bin — the phase
-  // (coded_sub_block_flag, a sig_coeff_flag, the DC flag, a greater1 flag, the greater2 flag) only chooses the context
-  // before the decision and the bookkeeping after it, and the bypass-coded rest of a sub-block (signs, remaining levels,
-  // the stores) is one more phase.  Lanes of a warp that sit at different places of different sub-blocks then share the
-  // decision itself, which is what the nested loops of rc_subblock cannot give them.  Bins are
-  // consumed in exactly the order of rc_subblock.
-  HEIC_HD void rc_levels(const Rc& r, int xs, int ys, uint32_t sig, uint32_t g1, int g2, int last_g1_pos) {
-    const int last_sig = 31 - HEIC_CLZ(sig);
-    const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
-    const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
-    const int n_sign = HEIC_POPC(sig) - (sign_hidden ? 1 : 0);
-    uint32_t sign_bits = n_sign ? fl_bypass(n_sign) << (32 - n_sign) : 0u;
-    int num_sig = 0, sum_abs = 0, rice = 0;
-    uint32_t m = sig;
-    while (m) {
-      int k = 31 - HEIC_CLZ(m);
-      m &= ~(1u << k);
-      int base = 1 + (int)((g1 >> k) & 1u) + ((k == last_g1_pos) ? g2 : 0);
-      int abs_level = base;
-      if (base == ((num_sig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
-        uint32_t rem = coeff_abs_level_remaining(rice);
-        if (rem > 32768u) {
-          fail(-3);
-          return;
-        }
-        abs_level = base + (int)rem;
-        if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
-      }
-      int v = (sign_bits >> 31) ? -abs_level : abs_level;
-      sign_bits <<= 1;
-      if (sign_hidden) {
-        sum_abs += abs_level;
-        if (k == first_sig && (sum_abs & 1)) v = -v;
-      }
-      uint32_t pxy = scan_xy(r.scan_idx, 2, k);
-      int xc = (xs << 2) + (int)(pxy & 15u), yc = (ys << 2) + (int)(pxy >> 4);
-      r.out[yc * r.n + xc] = (int16_t)clip3i(-32768, 32767, v);
-      num_sig++;
-    }
-  }
-  HEIC_HD void rc_run_fsm(Rc& r) {
-    enum { P_NEXT, P_CSBF, P_SIG, P_DC, P_AFTER_SIG, P_GT1, P_GT2, P_LEVELS, P_DONE };
-    const int c_idx = r.c_idx, log2 = r.log2;
-    int phase = P_NEXT;
-    int i = r.last_sub_block + 1;
-    int xs = 0, ys = 0, infer_sb_dc = 0, k = 0, add = 0, ctx_set = 0, num = 0, last_g1_pos = -1, g2 = 0;
-    uint32_t sig = 0, g1 = 0, m = 0;
-    uint64_t nib = 0;
-    for (;;) {
-      // ---- transitions that consume no context-coded bin (they may chain) ----
-      if (phase == P_LEVELS) {
-        rc_levels(r, xs, ys, sig, g1, g2, last_g1_pos);
-        phase = P_NEXT;
-      }
-      if (phase == P_NEXT) {
-        i--;
-        if (i < 0 || err) break;
-        const uint32_t sxy = scan_xy(r.scan_idx, r.lg_sb, i);
-        xs = (int)(sxy & 15u);
-        ys = (int)(sxy >> 4);
-        const int right = (xs < r.sb_w - 1) ? (int)((r.csbf >> (ys * 8 + xs + 1)) & 1u) : 0;
-        const int below = (ys < r.sb_w - 1) ? (int)((r.csbf >> ((ys + 1) * 8 + xs)) & 1u) : 0;
-        const int prev_csbf = right | (below << 1);
-        nib = tabs()->sig_nib[log2 == 2 ? r.scan_idx : 3 + r.scan_idx * 4 + prev_csbf];
-        add = r.sig_base + (log2 == 2 ? 0 : ((c_idx == 0 && (xs | ys)) ? 3 : 0) + r.sig_off);
-        sig = 0;
-        k = 15;
-        infer_sb_dc = 0;
-        if (i == r.last_sub_block) {
-          k = r.last_scan_pos - 1;
-          sig = 1u << r.last_scan_pos;
-        }
-        if (i < r.last_sub_block && i > 0) {
-          phase = P_CSBF;
-          k = CTX_CSBF + (c_idx ? 2 : 0) + (right | below);  // the flag's context, until the bin is there
-        } else {
-          r.csbf |= (uint64_t)1 << (ys * 8 + xs);
-          phase = k > 0 ? P_SIG : (k == 0 ? P_DC : P_AFTER_SIG);
-        }
-      }
-      if (phase == P_DC && infer_sb_dc && sig == 0) {
-        sig = 1u;  // inferred DC of a coded sub-block with no other significant coefficient
-        phase = P_AFTER_SIG;
-      }
-      if (phase == P_AFTER_SIG) {
-        if (!sig) {
-          phase = P_NEXT;
-          continue;
-        }
-        // 9.3.4.2.6 / 9.3.4.2.7: up to 8 greater1 flags, one greater2 flag
-        ctx_set = (i > 0 && c_idx == 0) ? 2 : 0;
-        if (!r.first_sub_block && r.greater1_ctx == 0) ctx_set++;
-        r.first_sub_block = 0;
-        r.greater1_ctx = 1;
-        g1 = 0;
-        g2 = 0;
-        m = sig;
-        num = 0;
-        last_g1_pos = -1;
-        phase = P_GT1;
-      }
-      // ---- one context-coded bin ----
-      int ctx;
-      if (phase == P_CSBF) ctx = k;
-      else if (phase == P_SIG) ctx = add + (int)((nib >> (4 * k)) & 15u);
-      else if (phase == P_DC) ctx = (log2 > 2 && i == 0) ? r.sig_base : add + (int)(nib & 15u);
-      else if (phase == P_GT1) ctx = CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2) + r.greater1_ctx;
-      else ctx = CTX_GT2 + (c_idx ? 4 : 0) + ctx_set;
-      const int bin = dec(ctx);
-      // ---- what the bin means ----
-      if (phase == P_CSBF) {
-        infer_sb_dc = 1;
-        k = 15;
-        if (bin) {
-          r.csbf |= (uint64_t)1 << (ys * 8 + xs);
-          phase = P_SIG;
-        } else {
-          phase = P_NEXT;
-        }
-      } else if (phase == P_SIG) {
-        if (bin) sig |= 1u << k;
-        if (--k == 0) phase = P_DC;
-      } else if (phase == P_DC) {
-        if (bin) sig |= 1u;
-        phase = P_AFTER_SIG;
-      } else if (phase == P_GT1) {
-        const int kk = 31 - HEIC_CLZ(m);
-        m &= ~(1u << kk);
-        num++;
-        if (bin) {
-          g1 |= 1u << kk;
-          r.greater1_ctx = 0;
-          if (last_g1_pos < 0) last_g1_pos = kk;
-        } else if (r.greater1_ctx > 0 && r.greater1_ctx < 3) {
-          r.greater1_ctx++;
-        }
-        if (!m || num == 8) phase = last_g1_pos >= 0 ? P_GT2 : P_LEVELS;
-      } else {
-        g2 = bin;
-        phase = P_LEVELS;
-      }
-    }
-    r.i = -1;
-  }
-#endif
   HEIC_HD int residual_coding(int log2, int c_idx, int pred_mode, int16_t* out) {
     Rc r;
     rc_begin(r, log2, c_idx, pred_mode, out);
-#if defined(HEIC_CABAC_FSM)
-    rc_run_fsm(r);
-#else
     for (; r.i >= 0 && !err; r.i--) rc_subblock(r);
-#endif
     return r.tskip;
   }
 
@@ -1222,83 +1065,6 @@ HEIC_NO_UNROLL
     return true;
   }
 
-#if defined(HEIC_CABAC_FLAT)
-  // EXPERIMENT, off by default (-DHEIC_CABAC_FLAT): the CTU walked as ONE loop whose iteration is "advance to the next
-  // coded 4x4 sub-block, then decode it", so that lanes of a warp holding 32 different pictures meet at every sub-block
-  // instead of at the end of every loop level of the nested form (below).  Bins are consumed in exactly the order of the
-  // nested form (tests/test_emul_parser.py runs both).  Measured on B200 it LOSES: 65.4 vs 58.9 ms per 592 images with
-  // copies of one tile in a warp and 427 vs 255 ms with 32 different tiles per warp -- the serialised header branches of
-  // the advance loop run once per sub-block for the whole warp, which costs more than the loop-level waits it removes.
-  HEIC_HD void coding_tree_unit(int rx, int ry) {
-    const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
-    const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
-    const int x_ctb = rx << log2_ctb, y_ctb = ry << log2_ctb;
-    if (!pp->cu_qp_delta_enabled) qp_y = tp->slice_qp;
-    if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
-    const uint32_t n_min = 1u << (2 * (log2_ctb - log2_min_cb));
-    enum { ST_CU, ST_TT, ST_COMP, ST_SB, ST_DONE };
-    int st = ST_CU, comp = 0;
-    uint32_t z = 0, z4_cu = 0;
-    Tt tt{};
-    Tu tu{};
-    Rc rc{};
-    for (;;) {
-      // ---- advance: everything between two sub-blocks ----
-      HEIC_NO_UNROLL
-      while (st != ST_SB && st != ST_DONE) {
-        if (err) {
-          st = ST_DONE;
-        } else if (st == ST_CU) {
-          if (z >= n_min) {
-            st = ST_DONE;
-          } else {
-            int x0, y0, log2;
-            if (ctu_next_cu(z, x_ctb, y_ctb, x0, y0, log2)) {
-              z4_cu = z << (2 * (log2_min_cb - 2));
-              z += 1u << (2 * (log2 - log2_min_cb));
-              cu_begin(x0, y0, log2);
-              tt_begin(tt);
-              st = ST_TT;
-            }
-          }
-        } else if (st == ST_TT) {
-          if (tt.z >= tt.n4) {
-            cu_end();
-            st = ST_CU;
-          } else {
-            tt_leaf(tt, tu, ctb_addr, z4_cu);
-            comp = 0;
-            st = ST_COMP;
-          }
-        } else {  // ST_COMP: next component of the transform unit with a residual
-          if (comp == 3) {
-            tu_end(tu);
-            tt.z += tt.step;
-            st = ST_TT;
-          } else {
-            int lg, pm;
-            int16_t* dst;
-            if (tu_component(tu, comp, lg, pm, dst)) {
-              rc_begin(rc, lg, comp, pm, dst);
-              st = ST_SB;
-            } else {
-              comp++;
-            }
-          }
-        }
-      }
-      if (st == ST_DONE || err) break;
-      // ---- one sub-block, all lanes that have one ----
-      rc_subblock(rc);
-      rc.i--;
-      if (rc.i < 0 || err) {
-        tu.ts |= (uint32_t)rc.tskip << comp;
-        comp++;
-        st = ST_COMP;
-      }
-    }
-  }
-#else
   HEIC_HD void coding_tree_unit(int rx, int ry) {
     const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
     const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
@@ -1332,7 +1098,6 @@ HEIC_NO_UNROLL
     }
 #endif
   }
-#endif
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -126,6 +126,8 @@ inline void make_tile_params(const dev::PicParams& pp, const heic_pps& pps, cons
   const heic_slice_header& sh = t.header;
   if (sh.slice_type != 2) bail(HEIC_E_UNSUPPORTED, "only I slices are supported");
   if (!t.rbsp || sh.slice_data_byte_offset > t.rbsp_len) bail(HEIC_E_INVALID_ARG, "slice data offset outside the RBSP");
+  if (sh.num_entry_point_offsets > HEIC_MAX_ENTRY_POINTS)  // substream_offset[] has HEIC_MAX_ENTRY_POINTS + 1 entries
+    bail(HEIC_E_UNSUPPORTED, "more entry points than heic_slice_header::substream_offset holds");
   if (pp.wpp && (int)sh.num_entry_point_offsets != pp.hctb - 1)
     bail(HEIC_E_UNSUPPORTED, "WPP picture without one entry point per CTB row");
   if (!pp.wpp && sh.num_entry_point_offsets != 0) bail(HEIC_E_UNSUPPORTED, "entry points without WPP (slices/tiles) are not supported");

@@ -503,11 +503,10 @@ cudaError_t launch_intra(const Arenas& A, const uint32_t* order, int max_log2_ct
   if (!A.n_tiles) return cudaSuccess;
   const IntraLayout L = intra_layout(max_log2_ctb);
   const size_t smem = (n_slots > 1 ? (((size_t)max_hctb * 4 + 15) & ~(size_t)15) : 0) + (size_t)n_slots * L.warp_bytes;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  // the opt-in is per device (and this library serves several devices per process): set it on every launch, it is cheap
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(intra_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
   intra_kernel<<<A.n_tiles, 32 * n_slots, smem, stream>>>(A, order, n_slots, L, clear_coeff ? 1 : 0);
   return cudaGetLastError();

@@ -111,7 +111,7 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
-  int probe_mix_k = 0, probe_mix_p = 0;  // measurement knob, see load()
+  int cabac_deal = 64;           // groups per dealing window of the size-sorted CABAC launch order, see load()
   int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
   int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
   int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
@@ -134,7 +134,7 @@ struct ImageInfo {
 };
 
 struct CabacClass {  // tiles launched together: same wavefront shape
-  int n_slots;
+  int n_slots, hctb;
   uint32_t order_off, n_groups;
 };
 
@@ -229,6 +229,12 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       bail(HEIC_E_INVALID_ARG, "image descriptor: n_tiles must equal grid_rows * grid_cols");
     PicParams pp;
     make_pic_params(im.sps, im.pps, pp);
+    // The colour/stitch stage crops from the picture origin: a conformance window is honoured when it only trims the
+    // right / bottom of a single picture (the canvas size does that); anything else would shift or mis-stitch the image.
+    if (im.sps.conformance_window_flag &&
+        (im.sps.conf_win_left_offset || im.sps.conf_win_top_offset ||
+         (im.n_tiles > 1 && (im.sps.conf_win_right_offset || im.sps.conf_win_bottom_offset))))
+      bail(HEIC_E_UNSUPPORTED, "conformance window with a left/top offset, or cropped grid tiles, is not supported");
     ScalingSet ss;
     build_scaling_set(im.sps, im.pps, ss);
     size_t s = 0;
@@ -326,18 +332,19 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   for (auto& kv : by_shape) {
     std::vector<uint32_t>& v = kv.second;
     std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tiles[a].bs_len > tiles[b].bs_len; });
-    if (ctx->probe_mix_k > 1 && ctx->probe_mix_p > 0) {
-      // Measurement knob (tools/cabac_divergence.py): a benchmark batch built from few distinct tiles puts copies of one
-      // tile into the 32 lanes of a warp.  Read blocks of k * p sorted entries (k runs of p copies) column by column, so
-      // that a warp holds k different tiles of neighbouring size instead.
-      const size_t k = (size_t)ctx->probe_mix_k, p = (size_t)ctx->probe_mix_p;
+    if (ctx->cabac_deal > 1 && tpc == 32 && v.size() > (size_t)tpc) {
+      // Deal the size-sorted list into groups with a stride: a window of `deal` groups' worth of neighbouring-size tiles
+      // is spread over `deal` groups (tile j of the window goes to group j % deal).  The lanes of a warp keep similar
+      // statistics (a window is a few per cent of a large batch), and up to `deal` byte-identical tiles -- copies of
+      // one picture in a batch, which a plain sort would put into one warp where they run converged and flatter the
+      // throughput -- end up in different warps.
       std::vector<uint32_t> w;
       w.reserve(v.size());
-      for (size_t b0 = 0; b0 < v.size(); b0 += k * p) {
-        const size_t n = std::min(k * p, v.size() - b0), rows = (n + p - 1) / p;
-        for (size_t c = 0; c < p; c++)
-          for (size_t r = 0; r < rows; r++)
-            if (r * p + c < n) w.push_back(v[b0 + r * p + c]);
+      const size_t win = (size_t)ctx->cabac_deal * (size_t)tpc;
+      for (size_t b0 = 0; b0 < v.size(); b0 += win) {
+        const size_t n = std::min(win, v.size() - b0), groups = (n + tpc - 1) / tpc;
+        for (size_t g = 0; g < groups; g++)
+          for (size_t j = g; j < n; j += groups) w.push_back(v[b0 + j]);
       }
       v.swap(w);
     }
@@ -357,10 +364,12 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       for (uint32_t t : v) order.push_back(t);
       c.n_groups = (uint32_t)v.size();
     } else {
+      // group_factor == 1 (default): every group takes the next 32 tiles of the size-sorted list, so all lanes are filled.
+      // group_factor > 1 additionally caps a group's slice bytes (heavy groups get fewer lanes; measured slower).
       uint64_t total = 0;
       for (uint32_t t : v) total += tiles[t].bs_len;
       const uint64_t target_groups = std::max<uint64_t>(1, (uint64_t)ctx->cabac_group_factor * ((v.size() + tpc - 1) / tpc));
-      const uint64_t w_target = std::max<uint64_t>(1, total / target_groups);
+      const uint64_t w_target = ctx->cabac_group_factor > 1 ? std::max<uint64_t>(1, total / target_groups) : ~(uint64_t)0;
       size_t i = 0;
       while (i < v.size()) {
         uint64_t wsum = 0;
@@ -375,6 +384,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
         c.n_groups++;
       }
     }
+    c.hctb = hctb;
     classes.push_back(c);
   }
 
@@ -471,7 +481,7 @@ void heic_b200_batch::run(uint32_t mask) {
     size_t ci = 0;
     for (const CabacClass& c : classes) {
       CU(launch_cabac(A, ctx->d_tabs, (const uint32_t*)((const uint8_t*)d_params.p + off_order) + c.order_off, c.n_groups, tiles_per_cta,
-                      c.n_slots, persistent ? (uint32_t*)d_counters.p + ci : nullptr, ctx->n_sm, ctx->cabac_resident, st));
+                      c.n_slots, (persistent && c.hctb > c.n_slots) ? (uint32_t*)d_counters.p + ci : nullptr, ctx->n_sm, ctx->cabac_resident, st));
       ctx->launches++;
       ci++;
     }
@@ -601,8 +611,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
     c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
     c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
-    c->probe_mix_k = env_int("HEIC_B200_PROBE_MIX_K", 0);
-    c->probe_mix_p = env_int("HEIC_B200_PROBE_MIX_P", 0);
+    c->cabac_deal = std::max(1, env_int("HEIC_B200_CABAC_DEAL", 64));
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;
@@ -678,13 +687,33 @@ int32_t heic_b200_batch_download_rgb(heic_b200_batch* b, uint8_t* rgb_out, size_
     if (!b || !rgb_out) bail(HEIC_E_INVALID_ARG, "null argument");
     CU(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->stream;
-    for (size_t i = 0; i < b->images.size(); i++) {
+    for (size_t i = 0; i < b->images.size(); i++) {  // validate the whole layout before the first copy is queued
       const ImageInfo& im = b->images[i];
       if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+      if (b->images.size() > 1 && (size_t)im.rot_h * pitch > image_stride)
+        bail(HEIC_E_INVALID_ARG, "image_stride smaller than one image (rows x pitch)");
+    }
+    for (size_t i = 0; i < b->images.size(); i++) {
+      const ImageInfo& im = b->images[i];
       CU(cudaMemcpy2DAsync(rgb_out + i * image_stride, pitch, (const uint8_t*)b->d_rgb.p + i * b->rgb_image_stride,
                            b->rgb_pitch, (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    return 0;
+  }));
+}
+
+// One image of a resident batch (bench.py / tools: pixel checks at batch sizes whose whole RGB output would not fit the host).
+int32_t heic_b200_batch_download_image(heic_b200_batch* b, uint32_t image_index, uint8_t* rgb_out, size_t pitch) {
+  return static_cast<int32_t>(guard([&]() -> int64_t {
+    if (!b || !rgb_out || image_index >= b->images.size()) bail(HEIC_E_INVALID_ARG, "invalid argument");
+    if (!b->d_rgb.p) bail(HEIC_E_INVALID_ARG, "the batch has no RGB output");
+    CU(cudaSetDevice(b->ctx->device));
+    const ImageInfo& im = b->images[image_index];
+    if (pitch < (size_t)im.rot_w * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+    CU(cudaMemcpy2DAsync(rgb_out, pitch, (const uint8_t*)b->d_rgb.p + (size_t)image_index * b->rgb_image_stride, b->rgb_pitch,
+                         (size_t)im.rot_w * 3, im.rot_h, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
     return 0;
   }));
 }
@@ -699,6 +728,17 @@ int32_t heic_b200_batch_status(heic_b200_batch* b, heic_tile_status* status) {
 }
 
 uint32_t heic_b200_batch_tile_count(const heic_b200_batch* b) { return b ? (uint32_t)b->tiles.size() : 0; }
+
+// CABAC launch order of a resident batch: tile indices, 32 per warp-group in the thread-per-substream mapping
+// (0xffffffff = idle lane).  Returns the number of entries; copies at most `cap` of them.  For tools and bench.py, which
+// checks that no warp holds two copies of one tile.
+size_t heic_b200_batch_cabac_order(const heic_b200_batch* b, uint32_t* out, size_t cap, uint32_t* tiles_per_group) {
+  if (!b) return 0;
+  if (tiles_per_group) *tiles_per_group = (uint32_t)b->tiles_per_cta;
+  if (out)
+    for (size_t i = 0; i < b->order.size() && i < cap; i++) out[i] = b->order[i];
+  return b->order.size();
+}
 
 int32_t heic_b200_batch_dump_tile(heic_b200_batch* b, uint32_t tile_index, heic_tile_dump* dump) {
   return static_cast<int32_t>(guard([&]() -> int64_t {
@@ -782,6 +822,12 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
     for (uint32_t t = 0; t < im.n_tiles; t++) make_tile_params(pp, im.pps, im.tiles[t], tp);
     const size_t ow = im.output_width ? im.output_width : (size_t)im.grid_cols * pp.w;
     const size_t oh = im.output_height ? im.output_height : (size_t)im.grid_rows * pp.h;
+    if (rgb_out) {  // the caller's buffer layout, checked for every image before anything is queued
+      const bool turn = apply_transforms && (im.rotation_ccw_quarter_turns & 1u);
+      const size_t rw = turn ? oh : ow, rh = turn ? ow : oh;
+      if (pitch < rw * 3) bail(HEIC_E_INVALID_ARG, "output pitch smaller than a row of RGB");
+      if (n_imgs > 1 && rh * pitch > image_stride) bail(HEIC_E_INVALID_ARG, "image_stride smaller than one image (rows x pitch)");
+    }
     first_tile[i + 1] = first_tile[i] + im.n_tiles;
     y_off[i + 1] = y_off[i] + ow * oh;
     c_off[i + 1] = c_off[i] + ((ow + 1) / 2) * ((oh + 1) / 2);
@@ -873,11 +919,13 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
   }
   } catch (...) {
     // a chunk could not be queued: retire the chunks of this job that are already in flight, then report
-    for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++)
-      if (ctx->pipe_pending[slot].job == job.get()) {
-        cudaStreamSynchronize(ctx->pipe_stream[slot]);
-        ctx->pipe_pending[slot].job = nullptr;
-      }
+    // (the failing chunk's slot has no pending entry yet but may already have copies queued into the caller's buffer:
+    // drain every idle slot's stream as well)
+    for (int slot = 0; slot < heic_b200_ctx::kPipe; slot++) {
+      if (!ctx->pipe_stream[slot]) continue;
+      if (ctx->pipe_pending[slot].job == job.get() || !ctx->pipe_pending[slot].job) cudaStreamSynchronize(ctx->pipe_stream[slot]);
+      if (ctx->pipe_pending[slot].job == job.get()) ctx->pipe_pending[slot].job = nullptr;
+    }
     throw;
   }
   if (trace)

@@ -94,6 +94,18 @@ void HeicDecoder::build_image(const HeifReader& reader, const Heif& heif, uint32
     std::vector<uint8_t> pps_rbsp = read_hvcc_nal_unit(first_nal_of_type(cfg, 34, "PPS").data, nullptr);
     out.desc.pps = picture_parameter_set_rbsp(pps_rbsp.data(), pps_rbsp.size());
   }
+  {
+    // HEIF 6.5.5: a 'colr' property of type nclx on the item overrides the colour description of the bitstream's VUI
+    const ItemProperty* colr = heif.property_of(item_id, fourcc("colr"));
+    if (colr && colr->colr_type == fourcc("nclx")) {
+      out.desc.sps.vui_parameters_present_flag = 1;
+      out.desc.sps.video_full_range_flag = colr->nclx_full_range;
+      out.desc.sps.matrix_coeffs = colr->nclx_matrix;
+      out.desc.sps.colour_primaries = colr->nclx_primaries;
+      out.desc.sps.transfer_characteristics = colr->nclx_transfer;
+    }
+    if (heif.property_of(item_id, fourcc("imir"))) bail(HEIC_E_UNSUPPORTED, "'imir' (mirroring) is not supported");
+  }
   const heic_sps& sps = out.desc.sps;
 
   out.rbsp.resize(tile_ids.size());

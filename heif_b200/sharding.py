@@ -1,6 +1,6 @@
 """Image sharding across the GPUs of one box.  Images (and the tiles inside them) are independent pictures
 (reference: the tile loop of src/heic/decoder.rs:98-119 has no cross-tile state), so every rank decodes its own
-contiguous block of the job and nothing crosses NVLink on the data path; torch.distributed is used only for the
+own images of the job (image_idx % n_gpus; or a contiguous block) and nothing crosses NVLink on the data path; torch.distributed is used only for the
 barrier around the timed region and for reducing the per-rank timings (max) and counters (sum)."""
 from __future__ import annotations
 
@@ -12,6 +12,13 @@ def shard_range(n_items: int, rank: int, world: int) -> range:
     base, extra = divmod(n_items, world)
     start = rank * base + min(rank, extra)
     return range(start, start + base + (1 if rank < extra else 0))
+
+
+def shard_modulo(n_items: int, rank: int, world: int) -> range:
+    """Round-robin partition of SURVEY section 8(e): item i belongs to rank i % world."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return range(rank, n_items, world)
 
 
 def reduce_timing(dist, device, elapsed_ms: float, counters: dict[str, float]):

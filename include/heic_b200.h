@@ -313,8 +313,13 @@ void*   heic_b200_batch_stream(heic_b200_batch* b);
 /* Device pointer + layout of the RGB output (image i at base + i*image_stride). */
 int32_t heic_b200_batch_rgb(heic_b200_batch* b, void** dev_ptr, size_t* pitch, size_t* image_stride);
 int32_t heic_b200_batch_download_rgb(heic_b200_batch* b, uint8_t* rgb_out, size_t pitch, size_t image_stride);
+/* RGB of one image of the batch (rows of rot_w*3 bytes, `pitch` apart) to host memory; synchronises the batch's stream. */
+int32_t heic_b200_batch_download_image(heic_b200_batch* b, uint32_t image_index, uint8_t* rgb_out, size_t pitch);
 int32_t heic_b200_batch_status(heic_b200_batch* b, heic_tile_status* status /* n_total_tiles */);
 uint32_t heic_b200_batch_tile_count(const heic_b200_batch* b);
+/* CABAC launch order of a resident batch (tools / bench.py): tile indices, *tiles_per_group (32 or 1) per CTA, 0xffffffff =
+ * idle lane.  Returns the number of entries and copies at most `cap` of them; `out` / `tiles_per_group` may be NULL. */
+size_t   heic_b200_batch_cabac_order(const heic_b200_batch* b, uint32_t* out, size_t cap, uint32_t* tiles_per_group);
 
 /* Intermediate buffers of one tile, copied to host, for per-stage parity tests.  Layouts are
  * documented in DESIGN.md ("Data layout in HBM").  Any pointer may be NULL.  The coefficient buffers hold levels

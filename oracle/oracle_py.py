@@ -115,6 +115,29 @@ def decode_picture(sps, pps, sh, rbsp, parse_only=False, intermediates=True):
     return res
 
 
+def decode_picture_into(sps, pps, sh, rbsp_ptr, rbsp_len, planes: np.ndarray):
+    """Final planes only, written straight into `planes` (uint8, Y then Cb then Cr, w*h*3/2 bytes): nothing but the C call
+    happens here, which is what bench.py's CPU arm times."""
+    lib = load()
+    w, h = sps.pic_width_in_luma_samples, sps.pic_height_in_luma_samples
+    out = OracleOut()
+    base = planes.ctypes.data
+    out.plane[0] = base
+    if sps.chroma_format_idc == 1:
+        out.plane[1] = base + w * h
+        out.plane[2] = base + w * h + (w // 2) * (h // 2)
+    rc = lib.hevc_oracle_decode_picture(C.byref(sps), C.byref(pps), C.byref(sh), C.cast(rbsp_ptr, C.c_void_p), rbsp_len, C.byref(out))
+    if rc < 0:
+        raise OracleError(rc, out.error.decode("utf-8", "replace"))
+    return out.bins
+
+
+def color_stitch_into(planes_ptr: int, grid_rows, grid_cols, tile_w, tile_h, out_w, out_h, full_range, matrix_coeffs, rgb_ptr: int,
+                      pitch: int):
+    load().hevc_oracle_color_stitch(planes_ptr, grid_rows, grid_cols, tile_w, tile_h, out_w, out_h, full_range, matrix_coeffs,
+                                    rgb_ptr, pitch)
+
+
 def color_stitch(planes: np.ndarray, grid_rows, grid_cols, tile_w, tile_h, out_w, out_h, full_range=1, matrix_coeffs=6):
     lib = load()
     planes = np.ascontiguousarray(planes, dtype=np.uint8)

@@ -207,7 +207,9 @@ extern "C" {
     ) -> i32;
     pub fn heic_b200_batch_download_rgb(b: *mut heic_b200_batch, rgb_out: *mut u8, pitch: usize, image_stride: usize) -> i32;
     pub fn heic_b200_batch_status(b: *mut heic_b200_batch, status: *mut heic_tile_status) -> i32;
+    pub fn heic_b200_batch_download_image(b: *mut heic_b200_batch, image_index: u32, rgb_out: *mut u8, pitch: usize) -> i32;
     pub fn heic_b200_batch_tile_count(b: *const heic_b200_batch) -> u32;
+    pub fn heic_b200_batch_cabac_order(b: *const heic_b200_batch, out: *mut u32, cap: usize, tiles_per_group: *mut u32) -> usize;
     pub fn heic_b200_batch_dump_tile(b: *mut heic_b200_batch, tile_index: u32, dump: *mut heic_tile_dump) -> i32;
     // ---- stand-alone stages on caller-owned buffers ----
     pub fn heic_b200_unescape(

@@ -362,8 +362,11 @@ int synth_encode_picture(const synth_config* cfg, uint64_t seed, uint8_t* out_vp
     std::memset(&tp, 0, sizeof tp);
     make_tile_params(pp, pps, td, tp);
 
-    static CabacTabs tabs;
-    build_cabac_tabs(tabs);
+    static const CabacTabs tabs = [] {  // built once (thread-safe: pool.py encodes from several threads)
+      CabacTabs t;
+      build_cabac_tabs(t);
+      return t;
+    }();
     std::vector<uint32_t> tu((size_t)pp.n_tu, 0), sao((size_t)pp.wctb * pp.hctb * 4, 0);
     std::vector<int16_t> l0((size_t)pp.n_tu * 16, 0), l1((size_t)pp.n_tu * 4, 0), l2((size_t)pp.n_tu * 4, 0);
     std::vector<uint8_t> ipm((size_t)pp.w4 * pp.h4, 0), ctd((size_t)pp.w8 * pp.h8, 0), qp((size_t)pp.w8 * pp.h8, 0), ctx(NUM_CTX_PAD);

@@ -94,19 +94,29 @@ class Picture:
 def encode(seed: int, **kw) -> Picture:
     """Deterministic: the same (seed, config) always yields the same bytes.  Retries the seed when the random walk hits a
     non-conformant value (rare; e.g. CuQpDeltaVal out of range)."""
+    nals, vals = _encode(seed, kw)
+    return Picture(nals, vals)
+
+
+def encode_nals(seed: int, **kw):
+    """The four NAL units (VPS, SPS, PPS, slice) of encode(seed, **kw) without parsing them; safe to call from threads."""
+    return _encode(seed, kw)[0]
+
+
+def _encode(seed: int, kw):
     lib = _load()
     vals = dict(DEFAULTS)
     vals.update(kw)
     if vals["cu_qp_delta"] and not vals["max_bypass_ones"]:
         vals["max_bypass_ones"] = 3
     cfg = Config(**vals)
-    cap = 8 << 20
+    cap = (1 << 20) if vals["width"] * vals["height"] <= 512 * 512 else (8 << 20)  # four output buffers of this size per call
     bufs = [C.create_string_buffer(cap) for _ in range(4)]
     lens = (C.c_size_t * 4)()
     for attempt in range(64):
         rc = lib.synth_encode_picture(C.byref(cfg), seed + 1000003 * attempt, *[C.cast(b, C.c_void_p) for b in bufs], cap, lens)
         if rc == 0:
-            return Picture([bufs[i].raw[: lens[i]] for i in range(4)], vals)
+            return [bufs[i].raw[: lens[i]] for i in range(4)], vals
         if rc != -3:
             raise ValueError(f"synth_encode_picture rejected the configuration (rc={rc}): {vals}")
     raise RuntimeError("no conformant random walk found in 64 attempts")

@@ -13,13 +13,12 @@ from oracle import oracle_py as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# "nested" is the walker the device runs; "flat" (HEIC_CABAC_FLAT: per-sub-block CTU loop) and "fsm" (HEIC_CABAC_FSM: one
-# context-coded bin per iteration inside a residual block) and "pos" (HEIC_CABAC_PAIR_BY_POSITION) are the opt-in
-# experiments of cabac_parse.cuh
-@pytest.fixture(scope="module", params=["nested", "flat", "fsm", "pos"])
+# "nested" is the plain walker; "pos" is the same with -DHEIC_CABAC_PAIR_BY_POSITION (coding units of a warp's lanes
+# paired by position instead of by index)
+@pytest.fixture(scope="module", params=["nested", "pos"])
 def emul(request):
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emul")])
-    name = {"nested": "libcabac_emul.so", "flat": "libcabac_emul_flat.so", "fsm": "libcabac_emul_fsm.so", "pos": "libcabac_emul_pos.so"}[request.param]
+    name = {"nested": "libcabac_emul.so", "pos": "libcabac_emul_pos.so"}[request.param]
     lib = C.CDLL(os.path.join(HERE, "emul", "_build", name))
     lib.emul_parse_picture.argtypes = ([C.POINTER(K.Sps), C.POINTER(K.Pps), C.POINTER(K.SliceHeader), C.c_void_p, C.c_uint32]
                                        + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)] * 2 + [C.c_int])
