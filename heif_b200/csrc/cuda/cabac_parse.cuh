@@ -116,6 +116,7 @@ struct Engine {
   }
   HEIC_HD bool offset_is_illegal() const { return (val >> 22) >= 510u; }
   HEIC_HD void expect_terminate(int) {}  // hook for the test-only encoder engine (tests/synth); nothing to do when decoding
+  HEIC_HD void hint_ctx(int) {}          // likewise: tells that engine which context the next decision uses
   HEIC_HD void refill() {
     if (nbits < 7) {
       val |= look0 << (6 - nbits);
@@ -408,6 +409,7 @@ struct Parser {
     return (int)r.v;
 #else
     uint32_t s = ld_ctx(idx);
+    e.hint_ctx(idx);
     const int bin = e.decision(tabs(), s);
     st_ctx(idx, s);
     return bin;
@@ -1073,22 +1075,6 @@ HEIC_NO_UNROLL
     if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
     const uint32_t n_min = 1u << (2 * (log2_ctb - log2_min_cb));
     uint32_t z = 0;
-#if defined(HEIC_CABAC_PAIR_BY_POSITION)
-    // EXPERIMENT, off by default until the GPU parity suite has run on it (bit-exact in the host emulation; on a B200 every
-    // tile of the bench batch decodes with a clean status and the CABAC stage takes 218 instead of 237 ms per 592 images
-    // with 32 different tiles per warp, 60.7 vs 60.3 ms converged): one pass over the CTB's
-    // minimum-size block positions, the same for every lane of a warp; a lane decodes the coding unit that starts at the
-    // position of the pass and idles otherwise.  The plain loop below pairs the lanes' coding units by INDEX, so a lane
-    // with sixteen 8x8 units meets the other lanes' 32x32 units sixteen times; by position it meets one.
-    // tools/cabac_divergence_model.py puts the gain at about 17 % of the CABAC time with 32 different tiles per warp.
-    for (uint32_t zz = 0; zz < n_min; zz++) {
-      if (zz != z || err) continue;
-      int x0, y0, log2;
-      if (!ctu_next_cu(z, x_ctb, y_ctb, x0, y0, log2)) continue;
-      coding_unit(x0, y0, log2, ctb_addr, zz << (2 * (log2_min_cb - 2)));
-      z += 1u << (2 * (log2 - log2_min_cb));
-    }
-#else
     while (z < n_min && !err) {
       int x0, y0, log2;
       const uint32_t z_cu = z;
@@ -1096,7 +1082,6 @@ HEIC_NO_UNROLL
       coding_unit(x0, y0, log2, ctb_addr, z_cu << (2 * (log2_min_cb - 2)));
       z += 1u << (2 * (log2 - log2_min_cb));
     }
-#endif
   }
 };
 

@@ -111,7 +111,7 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
-  int cabac_deal = 64;           // groups per dealing window of the size-sorted CABAC launch order, see load()
+  int cabac_deal = 128;          // groups per dealing window of the size-sorted CABAC launch order, see load()
   int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
   int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
   int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
@@ -335,14 +335,17 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
     if (ctx->cabac_deal > 1 && tpc == 32 && v.size() > (size_t)tpc) {
       // Deal the size-sorted list into groups with a stride: a window of `deal` groups' worth of neighbouring-size tiles
       // is spread over `deal` groups (tile j of the window goes to group j % deal).  The lanes of a warp keep similar
-      // statistics (a window is a few per cent of a large batch), and up to `deal` byte-identical tiles -- copies of
+      // statistics (a window is a few per cent of a large batch), and up to about `deal` byte-identical tiles -- copies of
       // one picture in a batch, which a plain sort would put into one warp where they run converged and flatter the
       // throughput -- end up in different warps.
       std::vector<uint32_t> w;
       w.reserve(v.size());
-      const size_t win = (size_t)ctx->cabac_deal * (size_t)tpc;
-      for (size_t b0 = 0; b0 < v.size(); b0 += win) {
-        const size_t n = std::min(win, v.size() - b0), groups = (n + tpc - 1) / tpc;
+      // windows of (about) `deal` groups each, all of the same size, so that the last one is not a short remainder
+      const size_t n_groups_all = (v.size() + tpc - 1) / tpc;
+      const size_t n_win = std::max<size_t>(1, (n_groups_all + ctx->cabac_deal / 2) / (size_t)ctx->cabac_deal);
+      for (size_t k = 0; k < n_win; k++) {
+        const size_t g0 = n_groups_all * k / n_win, g1 = n_groups_all * (k + 1) / n_win, groups = g1 - g0;
+        const size_t b0 = g0 * tpc, n = std::min(g1 * tpc, v.size()) - b0;
         for (size_t g = 0; g < groups; g++)
           for (size_t j = g; j < n; j += groups) w.push_back(v[b0 + j]);
       }
@@ -611,7 +614,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
     c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
     c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
-    c->cabac_deal = std::max(1, env_int("HEIC_B200_CABAC_DEAL", 64));
+    c->cabac_deal = std::max(1, env_int("HEIC_B200_CABAC_DEAL", 128));
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
     *out_ctx = c.release();
     return 0;

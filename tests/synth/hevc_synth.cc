@@ -67,6 +67,11 @@ struct EncEngine {
   Rng* rng = nullptr;
   double lps_gain = 1.0;          // > 1 makes LPS decisions more likely (busier streams)
   int max_bypass_ones = 6;        // caps unary / Exp-Golomb prefixes so values stay conformant
+  // Optional overrides of P(bin = 1) for two elements whose random-walk statistics are far from an encoder's choices
+  // (< 0: off, the context's own probability is used): real streams switch SAO on for a few per cent of the CTBs and
+  // smooth pictures rarely split their coding units.
+  double sao_on_prob = -1.0, split_cu_prob = -1.0;
+  int ctx_hint = -1;
   // arithmetic encoder state (9.3.4.x)
   uint32_t low = 0, range = 510;
   int first_bit = 1, outstanding = 0, ones_run = 0, next_term = 0;
@@ -142,7 +147,19 @@ struct EncEngine {
   }
   bool offset_is_illegal() const { return false; }
   void expect_terminate(int v) { next_term = v; }
+  void hint_ctx(int idx) { ctx_hint = idx; }
   int decision(const CabacTabs* T, uint32_t& s) {
+    double forced = -1.0;
+    if (ctx_hint == CTX_SAO_TYPE) forced = sao_on_prob;
+    else if (ctx_hint >= CTX_SPLIT_CU && ctx_hint < CTX_SPLIT_CU + 3) forced = split_cu_prob;
+    ctx_hint = -1;
+    if (forced >= 0.0) {
+      const int bin = rng->uniform() < forced ? 1 : 0;
+      encode_decision(T, s, bin);
+      bins++;
+      ones_run = 0;
+      return bin;
+    }
     // P(LPS) of pStateIdx p: 0.5 * alpha^p, alpha = (0.01875 / 0.5)^(1/63)
     const int p = (int)(s >> 1);
     double p_lps = 0.5;
@@ -278,6 +295,7 @@ struct synth_config {
   uint32_t full_range, matrix_coeffs;
   double lps_gain;                     // 1.0 = draw bins from the contexts' own probabilities
   uint32_t max_bypass_ones;
+  double sao_on_prob, split_cu_prob;   // < 0: unbiased (see EncEngine)
 };
 
 // Writes the four NAL units (2-byte header + escaped payload) of one IDR_N_LP picture.  Each out_* buffer has `cap`
@@ -375,6 +393,8 @@ int synth_encode_picture(const synth_config* cfg, uint64_t seed, uint8_t* out_vp
     P.e.rng = &rng;
     P.e.lps_gain = cfg->lps_gain > 0 ? cfg->lps_gain : 1.0;
     P.e.max_bypass_ones = cfg->max_bypass_ones ? (int)cfg->max_bypass_ones : 6;
+    P.e.sao_on_prob = cfg->sao_on_prob;
+    P.e.split_cu_prob = cfg->split_cu_prob;
     P.T = &tabs;
     P.ctx = ctx.data();
     P.pp = &pp;

@@ -22,16 +22,15 @@ FIXTURE_CODING = dict(width=512, height=512, chroma_format_idc=1, log2_min_cb=3,
                       init_qp_minus26=-11, cb_qp_offset=2, cr_qp_offset=2, wpp=1)
 
 
-def synth_params(k: int):
-    """(slice_qp_delta, lps_gain) of synthetic tile k.  A sweep sized to the fixture's bimodal 1.4-76 KB spread: 3 of 8
-    tiles are light (a few KB, like the fixture's sky tiles), 5 of 8 heavy (25-85 KB), every one with its own seed."""
+def synth_params(k: int) -> dict:
+    """Generator knobs of synthetic tile k.  A sweep sized to the fixture's bimodal 1.4-76 KB spread: 3 of 8 tiles are light
+    (a few KB and mostly unsplit coding units, like the fixture's sky tiles), 5 of 8 heavy (20-90 KB); every tile has its
+    own seed.  SAO is switched on for about 3 % of the CTBs, as in the fixture (0-4 % per tile); left to the random walk it
+    would be on for most CTBs, which no encoder produces."""
     if k % 8 < 3:
-        qd = (30, 33, 36)[k % 3]
-        gain = (0.2, 0.3, 0.4, 0.5, 0.6)[(k // 8) % 5]
-    else:
-        qd = (0, 2, 4, 6, 8, 10)[(k // 8) % 6]
-        gain = (0.7, 0.8, 0.9, 1.0, 1.1)[k % 5]
-    return qd, gain
+        return dict(slice_qp_delta=(20, 24, 28)[k % 3], lps_gain=(0.4, 0.5, 0.6, 0.7, 0.8)[(k // 8) % 5],
+                    split_cu_prob=(0.15, 0.25, 0.4)[(k // 3) % 3], sao_on_prob=0.03)
+    return dict(slice_qp_delta=(0, 2, 4, 6, 8, 10)[(k // 8) % 6], lps_gain=(0.8, 0.9, 1.0, 1.1, 1.2)[k % 5], sao_on_prob=0.03)
 
 
 class Pool:
@@ -66,8 +65,7 @@ def build_pool(heic_file, n_synth: int = 512, threads: int | None = None) -> Poo
     pool.keep.append(heic_file)
 
     def one(k):
-        qd, gain = synth_params(k)
-        return synth.encode_nals(1000 + k, slice_qp_delta=qd, lps_gain=gain, **FIXTURE_CODING)
+        return synth.encode_nals(1000 + k, **synth_params(k), **FIXTURE_CODING)
 
     synth._load()
     with ThreadPoolExecutor(threads or min(32, os.cpu_count() or 1)) as ex:

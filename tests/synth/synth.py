@@ -23,6 +23,7 @@ class Config(C.Structure):
         ("deblocking_disabled", C.c_uint32), ("beta_offset_div2", C.c_int32), ("tc_offset_div2", C.c_int32),
         ("slice_sao_luma", C.c_uint32), ("slice_sao_chroma", C.c_uint32), ("full_range", C.c_uint32),
         ("matrix_coeffs", C.c_uint32), ("lps_gain", C.c_double), ("max_bypass_ones", C.c_uint32),
+        ("sao_on_prob", C.c_double), ("split_cu_prob", C.c_double),
     ]
 
 
@@ -31,7 +32,7 @@ DEFAULTS = dict(width=128, height=128, chroma_format_idc=1, log2_min_cb=3, log2_
                 transform_skip=0, cu_qp_delta=0, diff_cu_qp_delta_depth=0, init_qp_minus26=0, slice_qp_delta=0, cb_qp_offset=0,
                 cr_qp_offset=0, slice_cb_qp_offset=0, slice_cr_qp_offset=0, wpp=1, deblocking_disabled=0, beta_offset_div2=0,
                 tc_offset_div2=0, slice_sao_luma=1, slice_sao_chroma=1, full_range=1, matrix_coeffs=6, lps_gain=1.0,
-                max_bypass_ones=0)
+                max_bypass_ones=0, sao_on_prob=-1.0, split_cu_prob=-1.0)
 
 _lib = None
 

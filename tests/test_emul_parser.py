@@ -13,12 +13,10 @@ from oracle import oracle_py as O
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-# "nested" is the plain walker; "pos" is the same with -DHEIC_CABAC_PAIR_BY_POSITION (coding units of a warp's lanes
-# paired by position instead of by index)
-@pytest.fixture(scope="module", params=["nested", "pos"])
+@pytest.fixture(scope="module", params=["nested"])
 def emul(request):
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emul")])
-    name = {"nested": "libcabac_emul.so", "pos": "libcabac_emul_pos.so"}[request.param]
+    name = {"nested": "libcabac_emul.so"}[request.param]
     lib = C.CDLL(os.path.join(HERE, "emul", "_build", name))
     lib.emul_parse_picture.argtypes = ([C.POINTER(K.Sps), C.POINTER(K.Pps), C.POINTER(K.SliceHeader), C.c_void_p, C.c_uint32]
                                        + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)] * 2 + [C.c_int])
