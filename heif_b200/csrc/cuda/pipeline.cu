@@ -135,7 +135,7 @@ struct ImageInfo {
 
 struct CabacClass {  // tiles launched together: same wavefront shape
   int n_slots, hctb;
-  uint32_t order_off, n_groups;
+  uint32_t order_off, n_groups, n_tiles;
 };
 
 struct heic_b200_batch {
@@ -388,6 +388,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       }
     }
     c.hctb = hctb;
+    c.n_tiles = (uint32_t)v.size();
     classes.push_back(c);
   }
 
