@@ -489,15 +489,42 @@ def main():
     value = world * args.steps * n_img * MP_PER_IMAGE / (ms * 1e-3)
     e2e_total = world * e2e_val
 
+    # ---- the same colour stage with the irot rotation applied (apply_transforms = 1; every iPhone portrait has one) ------------
+    rotated = None
+    if world == 1:
+        batch.close()
+        batch = None
+        n_rot = min(128, args.batch)
+        rb = dec.batch(images[:n_rot], apply_transforms=True)
+        rs = torch.cuda.ExternalStream(rb.stream, device=torch.device("cuda", local))
+        rb.decode()
+        rb.sync()
+        turns = int(images[0].rotation_ccw_quarter_turns) & 3
+        k0 = int(np.argmax(chk < n_rot)) if (chk < n_rot).any() else None
+        if k0 is not None:
+            got = rb.download_image(int(chk[k0]))
+            if not np.array_equal(got, np.rot90(ref_rgb[k0], turns)):
+                raise SystemExit(f"rotated output, image {int(chk[k0])}: differs from the rotated oracle image")
+        r0, r1 = ev(), ev()
+        r0.record(rs)
+        for _ in range(4):
+            rb.run(H.STAGE_SAO | H.STAGE_COLOR)
+        r1.record(rs)
+        rb.sync()
+        rot_ms = r0.elapsed_time(r1) / 4 / n_rot
+        rotated = {"quarter_turns_ccw": turns, "us_per_image": round(rot_ms * 1e3, 2), "us_per_image_unrotated": round(fused_ms / n_img * 1e3, 2),
+                   "ratio": round(rot_ms / (fused_ms / n_img), 3), "images": n_rot,
+                   "pixel_check": None if k0 is None else f"image {int(chk[k0])} == rot90(oracle image, {turns})"}
+        rb.close()
+
     # ---- upper bound for context: copies of ONE tile in every CABAC warp (what a batch of 48 repeated tiles measures) ----
     converged = None
     if world == 1 and not args.no_converged:
-        batch.close()
         rng = np.random.default_rng(SEED)
         perm_ids = np.stack([rng.permutation(48) for _ in range(args.batch)])  # real tiles only, 592 copies of each
-        os.environ["HEIC_B200_CABAC_DEAL"] = "1"  # plain size sort: the copies of a tile land in the same warps
+        os.environ["HEIC_B200_CABAC_PLAIN_SORT"] = "1"  # plain size sort: the copies of a tile land in the same warps
         dec2 = H.HeicDecoder(device=local)
-        del os.environ["HEIC_B200_CABAC_DEAL"]
+        del os.environ["HEIC_B200_CABAC_PLAIN_SORT"]
         imgs2, keep2 = [], []
         tsize = C.sizeof(H._capi.TileDesc)
         for i in range(args.batch):
@@ -529,7 +556,6 @@ def main():
                              "every CABAC warp holds 32 copies of one tile and never diverges (round 1's headline)"}
         b2.close()
         dec2.close()
-        batch = None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -581,6 +607,7 @@ def main():
                     "images_per_call": eb, "host_affinity": affinity, "ms_per_call": round(e2e_s * 1e3, 3), "host_submit_ms_per_call": round(submit_s / e2e_steps * 1e3, 3),
                     "mode": "double-buffered heic_b200_decode_grids_submit/_job_wait, pinned host RGB",
                     "synchronous_call_MPps": round(world * eb * MP_PER_IMAGE / sync_s, 2)},
+            "rotated_color": rotated,
             "copies_per_warp_upper_bound": converged,
             "gpu_launches": int(launches),
             "clocks": clk,

@@ -173,13 +173,14 @@ def _desc_array(images):
 class Batch:
     """A resident batch: bitstreams, descriptors and every intermediate live in HBM (heic_b200_batch_*)."""
 
-    def __init__(self, dec: "HeicDecoder", images):
+    def __init__(self, dec: "HeicDecoder", images, apply_transforms: bool = False):
         self._lib = dec._lib
         self._dec = dec
         self.images = list(images)
+        self.apply_transforms = bool(apply_transforms)
         self._arr = _desc_array(self.images)
         self._h = C.c_void_p()
-        K.check(self._lib.heic_b200_batch_create(dec._h, self._arr, len(self.images), C.byref(self._h)))
+        K.check(self._lib.heic_b200_batch_create_ex(dec._h, self._arr, len(self.images), int(self.apply_transforms), C.byref(self._h)))
 
     def close(self):
         if self._h:
@@ -229,7 +230,7 @@ class Batch:
         return int(p.value or 0), pitch.value, stride.value
 
     def download_rgb(self, out: np.ndarray | None = None) -> np.ndarray:
-        w, h = _canvas(self.images[0], False)
+        w, h = _canvas(self.images[0], self.apply_transforms)
         if out is None:
             out = np.empty((len(self.images), h, w, 3), np.uint8)
         K.check(self._lib.heic_b200_batch_download_rgb(self._h, out.ctypes.data, out.strides[1], out.strides[0]))
@@ -237,7 +238,7 @@ class Batch:
 
     def download_image(self, index: int) -> np.ndarray:
         """RGB of one image of the batch (H, W, 3)."""
-        w, h = _canvas(self.images[index], False)
+        w, h = _canvas(self.images[index], self.apply_transforms)
         out = np.empty((h, w, 3), np.uint8)
         K.check(self._lib.heic_b200_batch_download_image(self._h, index, out.ctypes.data, out.strides[0]))
         return out
@@ -375,8 +376,8 @@ class HeicDecoder:
             co += cw * ch
         return res
 
-    def batch(self, images) -> Batch:
-        return Batch(self, images)
+    def batch(self, images, apply_transforms: bool = False) -> Batch:
+        return Batch(self, images, apply_transforms)
 
     def color_stitch(self, dev_planes: int, n_images, grid_rows, grid_cols, tile_w, tile_h, out_w, out_h, dev_rgb: int,
                      pitch: int, image_stride: int, full_range: int = 1, matrix_coeffs: int = 6):

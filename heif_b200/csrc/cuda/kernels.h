@@ -39,6 +39,9 @@ cudaError_t launch_deblock(const Arenas& A, uint32_t max_w, uint32_t max_h, cuda
 
 // Stage 5 — SAO (8.7.3): recon arena -> final arena.
 cudaError_t launch_sao(const Arenas& A, uint32_t max_pitch, uint32_t max_h, cudaStream_t stream);
+// The same for the CTBs with SAO switched on only (the others are left untouched in the final arena): what a decode to RGB
+// runs, followed by a colour kernel that picks every CTB's component from the arena holding its final samples.
+cudaError_t launch_sao_sparse(const Arenas& A, int max_hctb, cudaStream_t stream);
 
 // Stage 6 — YCbCr 4:2:0 -> RGB8 + grid stitch + crop (+ irot).
 struct ColorJob {
@@ -55,8 +58,10 @@ struct ColorJob {
   uint32_t rotation;            // ccw quarter turns applied to the output
   uint8_t* rgb;
   uint64_t pitch, image_stride; // output layout in bytes
-  // fused == 1: `planes` is the deblocked reconstruction and SAO (8.7.3) is applied on the way in
+  // fused == 1: `planes` is the deblocked reconstruction, and a CTB component whose SAO type is non-zero is read from
+  // `planes_sao` instead (the final arena, same layout, filled for those CTBs by launch_sao_sparse)
   uint32_t fused;
+  const uint8_t* planes_sao;
   const uint32_t* sao;          // SAO parameters of the job's first tile (4 words per CTB; all-zero where SAO is off)
   uint32_t sao_stride;          // words between tiles
   uint32_t log2_ctb, wctb;

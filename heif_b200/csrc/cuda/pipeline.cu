@@ -96,6 +96,9 @@ struct heic_b200_job {
 struct PipePending {
   heic_b200_job* job = nullptr;  // null: slot idle
   size_t tile0 = 0, n_tiles = 0;
+  // HEIC_B200_TRACE=2: device timeline of the chunk (events: queued, slice data on the device, CABAC done, kernels done, RGB on the host)
+  cudaEvent_t ev[5] = {};
+  double host_ms = 0;  // host time at which the chunk was queued
 };
 
 struct heic_b200_ctx {
@@ -111,15 +114,16 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
-  int cabac_deal = 128;          // groups per dealing window of the size-sorted CABAC launch order, see load()
+  int cabac_plain_sort = 0;      // measurement knob: plain size sort, copies of a slice may share a warp (bench.py's upper bound)
   int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
   int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
   int fuse_sao = 1;              // full decodes to RGB apply SAO inside the colour kernel (no `final` planes round trip)
   // decode_grids pipeline: chunks of `pipe_chunk` images rotate over up to kPipe slots, each with its own stream and
   // scratch batch, so the H2D copy, the kernels and the D2H copy of different chunks overlap
-  static constexpr int kPipe = 8;
-  int pipe_chunk = 32;
-  int pipe_slots = kPipe;
+  static constexpr int kPipe = 16;
+  int pipe_chunk = 0;   // images per chunk; 0: automatic (see submit_grids)
+  int pipe_slots = 0;   // chunks in flight; 0: automatic
+  cudaEvent_t trace_base = nullptr;  // HEIC_B200_TRACE=2: time zero of the chunk timelines
   cudaStream_t pipe_stream[kPipe] = {};
   std::unique_ptr<heic_b200_batch> pipe_batch[kPipe];
   PipePending pipe_pending[kPipe];
@@ -194,7 +198,10 @@ struct heic_b200_batch {
 };
 
 heic_b200_ctx::~heic_b200_ctx() {
+  if (trace_base) cudaEventDestroy(trace_base);
   for (int i = 0; i < kPipe; i++) {
+    for (cudaEvent_t e : pipe_pending[i].ev)
+      if (e) cudaEventDestroy(e);
     pipe_batch[i].reset();
     if (pipe_stream[i]) cudaStreamDestroy(pipe_stream[i]);
   }
@@ -324,6 +331,25 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   // (the GPU is mostly empty either way); many tiles: thread per substream is 11x the throughput
   tiles_per_cta = (ctx->cabac_tiles_per_cta == 32 && n_tiles_hint > (size_t)ctx->low_latency_tiles) ? 32 : 1;
   const int tpc = tiles_per_cta;
+  // content fingerprint of every slice (four 8-byte samples): equal length + equal fingerprint = "the same picture again"
+  std::vector<uint64_t> fingerprint(tiles.size(), 0);
+  {
+    size_t t = 0;
+    for (uint32_t i = 0; i < n_imgs; i++)
+      for (uint32_t k = 0; k < imgs[i].n_tiles; k++, t++) {
+        const uint8_t* p = imgs[i].tiles[k].rbsp;
+        const size_t len = imgs[i].tiles[k].rbsp_len;
+        uint64_t h = 0x9e3779b97f4a7c15ull ^ len;
+        if (len >= 8)
+          for (int q = 0; q < 4; q++) {
+            uint64_t w8;
+            std::memcpy(&w8, p + (len - 8) * q / 3, 8);
+            h = (h ^ w8) * 0xbf58476d1ce4e5b9ull;
+            h ^= h >> 29;
+          }
+        fingerprint[t] = h;
+      }
+  }
   std::map<std::tuple<int, int, int, int>, std::vector<uint32_t>> by_shape;
   for (uint32_t t = 0; t < tiles.size(); t++) {
     const PicParams& pp = pics[tiles[t].pic];
@@ -331,26 +357,9 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   }
   for (auto& kv : by_shape) {
     std::vector<uint32_t>& v = kv.second;
-    std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) { return tiles[a].bs_len > tiles[b].bs_len; });
-    if (ctx->cabac_deal > 1 && tpc == 32 && v.size() > (size_t)tpc) {
-      // Deal the size-sorted list into groups with a stride: a window of `deal` groups' worth of neighbouring-size tiles
-      // is spread over `deal` groups (tile j of the window goes to group j % deal).  The lanes of a warp keep similar
-      // statistics (a window is a few per cent of a large batch), and up to about `deal` byte-identical tiles -- copies of
-      // one picture in a batch, which a plain sort would put into one warp where they run converged and flatter the
-      // throughput -- end up in different warps.
-      std::vector<uint32_t> w;
-      w.reserve(v.size());
-      // windows of (about) `deal` groups each, all of the same size, so that the last one is not a short remainder
-      const size_t n_groups_all = (v.size() + tpc - 1) / tpc;
-      const size_t n_win = std::max<size_t>(1, (n_groups_all + ctx->cabac_deal / 2) / (size_t)ctx->cabac_deal);
-      for (size_t k = 0; k < n_win; k++) {
-        const size_t g0 = n_groups_all * k / n_win, g1 = n_groups_all * (k + 1) / n_win, groups = g1 - g0;
-        const size_t b0 = g0 * tpc, n = std::min(g1 * tpc, v.size()) - b0;
-        for (size_t g = 0; g < groups; g++)
-          for (size_t j = g; j < n; j += groups) w.push_back(v[b0 + j]);
-      }
-      v.swap(w);
-    }
+    std::stable_sort(v.begin(), v.end(), [&](uint32_t a, uint32_t b) {
+      return tiles[a].bs_len != tiles[b].bs_len ? tiles[a].bs_len > tiles[b].bs_len : fingerprint[a] < fingerprint[b];
+    });
     const int wpp = std::get<0>(kv.first), wctb = std::get<1>(kv.first), hctb = std::get<2>(kv.first);
     CabacClass c;
     // with the two-CTU WPP lag at most ceil(wctb / 2) rows of a picture are in flight
@@ -367,24 +376,57 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
       for (uint32_t t : v) order.push_back(t);
       c.n_groups = (uint32_t)v.size();
     } else {
-      // group_factor == 1 (default): every group takes the next 32 tiles of the size-sorted list, so all lanes are filled.
-      // group_factor > 1 additionally caps a group's slice bytes (heavy groups get fewer lanes; measured slower).
-      uint64_t total = 0;
-      for (uint32_t t : v) total += tiles[t].bs_len;
-      const uint64_t target_groups = std::max<uint64_t>(1, (uint64_t)ctx->cabac_group_factor * ((v.size() + tpc - 1) / tpc));
-      const uint64_t w_target = ctx->cabac_group_factor > 1 ? std::max<uint64_t>(1, total / target_groups) : ~(uint64_t)0;
-      size_t i = 0;
-      while (i < v.size()) {
-        uint64_t wsum = 0;
-        int n = 0;
-        while (i < v.size() && n < tpc && (n == 0 || wsum + tiles[v[i]].bs_len <= w_target)) {
-          wsum += tiles[v[i]].bs_len;
-          order.push_back(v[i]);
-          i++;
-          n++;
+      if (ctx->cabac_group_factor == 1) {
+        // Groups of 32 tiles of neighbouring slice size, NO TWO OF THEM BYTE-IDENTICAL.  The sorted list is seen as runs of
+        // identical slices (same length and same content fingerprint; a batch of distinct pictures has runs of one, and the
+        // groups are then simply consecutive blocks of the sorted list).  A group takes one tile from each of the first 32
+        // runs that still have one, so copies of a picture -- which would run converged in one warp and flatter the
+        // throughput, as a benchmark batch built from few distinct tiles does -- always land in different warps, while the
+        // lanes of a warp stay as similar in size as the input allows.
+        struct Run {
+          size_t first, left;
+        };
+        std::vector<Run> runs;
+        for (size_t i = 0; i < v.size();) {
+          size_t j = i + 1;
+          while (!ctx->cabac_plain_sort && j < v.size() && tiles[v[j]].bs_len == tiles[v[i]].bs_len && fingerprint[v[j]] == fingerprint[v[i]]) j++;
+          runs.push_back({i, j - i});
+          i = j;
         }
-        for (; n < tpc; n++) order.push_back(0xffffffffu);
-        c.n_groups++;
+        size_t head = 0;  // runs before `head` are exhausted
+        while (head < runs.size()) {
+          int n = 0;
+          for (size_t r = head; r < runs.size() && n < tpc; r++) {
+            if (!runs[r].left) continue;
+            order.push_back(v[runs[r].first++]);
+            runs[r].left--;
+            n++;
+          }
+          while (head < runs.size() && !runs[head].left) head++;
+          if (!n) break;
+          for (; n < tpc; n++) order.push_back(0xffffffffu);
+          c.n_groups++;
+        }
+      } else {
+        // group_factor > 1: the sorted list cut into groups of about equal slice bytes (heavy groups get fewer lanes; measured
+        // slower: a CTA costs its critical-path lane, not the sum of its lanes)
+        uint64_t total = 0;
+        for (uint32_t t : v) total += tiles[t].bs_len;
+        const uint64_t target_groups = std::max<uint64_t>(1, (uint64_t)ctx->cabac_group_factor * ((v.size() + tpc - 1) / tpc));
+        const uint64_t w_target = std::max<uint64_t>(1, total / target_groups);
+        size_t i = 0;
+        while (i < v.size()) {
+          uint64_t wsum = 0;
+          int n = 0;
+          while (i < v.size() && n < tpc && (n == 0 || wsum + tiles[v[i]].bs_len <= w_target)) {
+            wsum += tiles[v[i]].bs_len;
+            order.push_back(v[i]);
+            i++;
+            n++;
+          }
+          for (; n < tpc; n++) order.push_back(0xffffffffu);
+          c.n_groups++;
+        }
       }
     }
     c.hctb = hctb;
@@ -512,7 +554,12 @@ void heic_b200_batch::run(uint32_t mask) {
     final_stale = false;
     ctx->launches++;
   }
-  if (fuse) final_stale = true;
+  if (fuse) {
+    // SAO for the few CTBs that have it on, into the final arena; the colour kernel picks per CTB and component
+    CU(launch_sao_sparse(A, max_hctb, st));
+    ctx->launches++;
+    final_stale = true;
+  }
   if ((mask & HEIC_STAGE_COLOR) && d_rgb.p) {
     // consecutive images of identical geometry go out in one launch
     size_t i = 0;
@@ -530,6 +577,7 @@ void heic_b200_batch::run(uint32_t mask) {
       ColorJob job;
       job.planes = (const uint8_t*)(fuse ? d_recon.p : d_final.p) + t0.plane_off[0];
       job.fused = fuse ? 1u : 0u;
+      job.planes_sao = (const uint8_t*)d_final.p + t0.plane_off[0];
       job.sao = A.sao + t0.sao_off;
       job.sao_stride = (uint32_t)((size_t)pp.wctb * pp.hctb * 4);
       job.log2_ctb = (uint32_t)pp.log2_ctb;
@@ -610,13 +658,13 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_slots = env_int("HEIC_B200_CABAC_SLOTS", 0);
     c->intra_slots = std::min(8, env_int("HEIC_B200_INTRA_SLOTS", 0));
     c->cabac_group_factor = std::max(1, env_int("HEIC_B200_CABAC_GROUP_FACTOR", 1));
-    c->pipe_chunk = std::max(1, env_int("HEIC_B200_PIPE_CHUNK", 32));
+    c->pipe_chunk = std::max(0, env_int("HEIC_B200_PIPE_CHUNK", 0));
     c->low_latency_tiles = env_int("HEIC_B200_LOW_LATENCY_TILES", 384);
     c->fuse_sao = env_int("HEIC_B200_FUSE_SAO", 1) != 0;
     c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
     c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
-    c->cabac_deal = std::max(1, env_int("HEIC_B200_CABAC_DEAL", 128));
-    c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(1, env_int("HEIC_B200_PIPE_SLOTS", heic_b200_ctx::kPipe)));
+    c->cabac_plain_sort = env_int("HEIC_B200_CABAC_PLAIN_SORT", 0) != 0;
+    c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(0, env_int("HEIC_B200_PIPE_SLOTS", 0)));
     *out_ctx = c.release();
     return 0;
   }));
@@ -632,6 +680,11 @@ void heic_b200_destroy(heic_b200_ctx* ctx) {
 uint64_t heic_b200_launch_count(const heic_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, heic_b200_batch** out) {
+  return heic_b200_batch_create_ex(ctx, imgs, n_imgs, 0, out);
+}
+
+int32_t heic_b200_batch_create_ex(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, int32_t apply_transforms,
+                                  heic_b200_batch** out) {
   return static_cast<int32_t>(guard([&]() -> int64_t {
     if (!ctx || !imgs || !out || !n_imgs) bail(HEIC_E_INVALID_ARG, "null argument");
     *out = nullptr;
@@ -639,7 +692,7 @@ int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, 
     auto b = std::make_unique<heic_b200_batch>();
     b->ctx = ctx;
     b->stream = ctx->stream;
-    b->apply_transforms = false;
+    b->apply_transforms = apply_transforms != 0;
     b->load(imgs, n_imgs, true);
     CU(cudaStreamSynchronize(ctx->stream));
     *out = b.release();
@@ -798,6 +851,12 @@ static void harvest_slot(heic_b200_ctx* ctx, int slot) {
   if (!pd.job) return;
   heic_b200_batch* b = ctx->pipe_batch[slot].get();
   CU(cudaStreamSynchronize(b->stream));
+  if (pd.ev[0] && ctx->trace_base) {
+    float t[5];
+    for (int k = 0; k < 5; k++) cudaEventElapsedTime(&t[k], ctx->trace_base, pd.ev[k]);
+    std::fprintf(stderr, "[heic_b200] chunk slot %2d tiles %6zu: queued %8.1f  h2d %8.1f  cabac %8.1f  kernels %8.1f  d2h %8.1f ms\n", slot,
+                 pd.n_tiles, t[0], t[1], t[2], t[3], t[4]);
+  }
   const TileStatusDev* s = (const TileStatusDev*)b->h_status.p;
   heic_tile_status* out = pd.job->status + pd.tile0;
   for (size_t i = 0; i < pd.n_tiles; i++) {
@@ -837,6 +896,7 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
     c_off[i + 1] = c_off[i] + ((ow + 1) / 2) * ((oh + 1) / 2);
   }
   static const bool trace = std::getenv("HEIC_B200_TRACE") != nullptr;  // host-side phase times of a submit, to stderr
+  static const bool trace2 = trace && std::atoi(std::getenv("HEIC_B200_TRACE")) >= 2;  // + the device timeline of every chunk
   using clk = std::chrono::steady_clock;
   auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
   const clk::time_point t_call = clk::now();
@@ -851,14 +911,25 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
   }
   // equal chunks (a ramp of small first chunks was measured slower: every chunk pays the CABAC latency floor of its
   // heaviest tiles while holding a pipeline slot)
-  const uint32_t chunk = (uint32_t)std::max(1, ctx->pipe_chunk);
+  // Chunk size.  The CABAC stage is latency-bound per 32-tile group (a group lasts as long as its heaviest tile's critical
+  // path, ~100 ms for a 70 KB slice), so a chunk only uses the machine when it brings about as many groups as CTAs are
+  // resident (444 groups = 296 images of 48 tiles): measured on B200, eight 32-image chunks in flight decode at 10.4 K MP/s,
+  // one 256-image chunk per call, double-buffered, at the speed of a resident 256-image batch.  So by default a call is cut
+  // into equal chunks of at most 296 images, and two or three such chunks rotate (the next call's kernels run while this
+  // call's RGB travels to the host); HEIC_B200_PIPE_CHUNK / _SLOTS override.
+  uint32_t chunk = (uint32_t)std::max(0, ctx->pipe_chunk);
+  if (chunk == 0) {
+    const uint32_t parts = (n_imgs + 295u) / 296u;
+    chunk = (n_imgs + parts - 1) / parts;
+  }
+  const uint32_t n_slots_use = ctx->pipe_slots > 0 ? (uint32_t)ctx->pipe_slots : std::min(8u, std::max(2u, 600u / chunk));
   std::vector<uint32_t> chunk_start;
   for (uint32_t i = 0; i < n_imgs; i += chunk) chunk_start.push_back(i);
   chunk_start.push_back(n_imgs);
   const uint32_t n_chunks = (uint32_t)chunk_start.size() - 1;
   try {
   for (uint32_t k = 0; k < n_chunks; k++) {
-    const int slot = (int)(ctx->pipe_next++ % (uint32_t)ctx->pipe_slots);
+    const int slot = (int)(ctx->pipe_next++ % n_slots_use);
     const uint32_t i0 = chunk_start[k], cnt = chunk_start[k + 1] - i0;
     if (!ctx->pipe_stream[slot]) CU(cudaStreamCreateWithFlags(&ctx->pipe_stream[slot], cudaStreamNonBlocking));
     if (!ctx->pipe_batch[slot]) {
@@ -876,7 +947,25 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
     b->load(imgs + i0, cnt, rgb_out != nullptr);
     t_load += ms_since(t0);
     t0 = clk::now();
-    b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
+    PipePending& pend = ctx->pipe_pending[slot];
+    if (trace2) {
+      if (!ctx->trace_base) {
+        CU(cudaEventCreate(&ctx->trace_base));
+        CU(cudaEventRecord(ctx->trace_base, st));
+      }
+      for (int e = 0; e < 5; e++)
+        if (!pend.ev[e]) CU(cudaEventCreate(&pend.ev[e]));
+      // (the H2D copies were queued by load(): "queued" is recorded behind them, so h2d - queued is not their duration;
+      // the columns that matter are when CABAC, the other kernels and the D2H copy of this chunk END)
+      CU(cudaEventRecord(pend.ev[0], st));
+      CU(cudaEventRecord(pend.ev[1], st));
+      b->run(HEIC_STAGE_CABAC);
+      CU(cudaEventRecord(pend.ev[2], st));
+      b->run((rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR)) & ~HEIC_STAGE_CABAC);
+      CU(cudaEventRecord(pend.ev[3], st));
+    } else {
+      b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
+    }
     t_run += ms_since(t0);
     if (rgb_out) {
       bool one_copy = image_stride == b->rgb_image_stride && pitch == b->rgb_pitch;
@@ -917,6 +1006,7 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
       }
     }
     CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, b->tiles.size() * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
+    if (trace2) CU(cudaEventRecord(pend.ev[4], st));
     ctx->pipe_pending[slot].job = job.get();
     ctx->pipe_pending[slot].tile0 = first_tile[i0];
     ctx->pipe_pending[slot].n_tiles = b->tiles.size();
@@ -1068,6 +1158,7 @@ int32_t heic_b200_color_stitch(heic_b200_ctx* ctx, const void* dev_planes, uint3
     ColorJob job;
     job.planes = (const uint8_t*)dev_planes;
     job.fused = 0;
+    job.planes_sao = nullptr;
     job.sao = nullptr;
     job.sao_stride = 0;
     job.log2_ctb = job.wctb = 0;

@@ -67,7 +67,53 @@ __global__ void __launch_bounds__(256) sao_kernel(Arenas A, uint32_t blocks_per_
   }
 }
 
+// Sparse form for the RGB path: only the CTBs whose SAO type is non-zero (a few per cent in real streams) are processed,
+// recon arena -> final arena at those CTBs; the colour kernel then reads each CTB's component from whichever arena holds
+// its final samples.  One CTA per CTB row of a tile, a warp per CTB (round-robin); a warp whose CTB has SAO off leaves after
+// one 16-byte load of the CTB's parameter words.
+__global__ void __launch_bounds__(128) sao_sparse_kernel(Arenas A, uint32_t max_hctb) {
+  const uint32_t tile = blockIdx.x / max_hctb, ry = blockIdx.x % max_hctb;
+  const TileParams* tp = A.tiles + tile;
+  const PicParams* pp = A.pics + tp->pic;
+  if (A.status[tile].code != 0 || ry >= (uint32_t)pp->hctb) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_comp = pp->chroma ? 3 : 1;
+  for (int rx = warp; rx < pp->wctb; rx += 4) {
+    const uint4 sp = *reinterpret_cast<const uint4*>(A.sao + tp->sao_off + (size_t)(ry * pp->wctb + rx) * 4);
+    if (!((sp.x | sp.y | sp.z) & 3u)) continue;
+#pragma unroll 1
+    for (int c = 0; c < n_comp; c++) {
+      const uint32_t word = c == 0 ? sp.x : (c == 1 ? sp.y : sp.z);
+      if (!(word & 3u)) continue;
+      const int sub = c ? 1 : 0;
+      const int cs = 1 << (pp->log2_ctb - sub), pw = pp->w >> sub, ph = pp->h >> sub, pitch = c ? pp->pitch_c : pp->pitch_y;
+      const int x_ctb = rx * cs, y_ctb = (int)ry * cs;
+      const uint8_t* src = A.recon + tp->plane_off[c];
+      uint8_t* dst = A.final_ + tp->plane_off[c];
+      const int gpr = cs >> 3;  // 8-sample groups per CTB row
+#pragma unroll 1
+      for (int it = lane; it < gpr * cs; it += 32) {
+        const int x = x_ctb + (it % gpr) * 8, y = y_ctb + it / gpr;
+        if (x >= pw || y >= ph) continue;
+        const uint8_t* row = src + (size_t)y * pitch;
+        const uint2 in = *reinterpret_cast<const uint2*>(row + x);  // pitches are multiples of 64: inside the row
+        uint32_t o[2] = {in.x, in.y};
+        sao8(o, row, x, y, pw, ph, pitch, word, (int)(word & 3u));
+        uint8_t* out = dst + (size_t)y * pitch + x;
+        *reinterpret_cast<uint32_t*>(out) = o[0];
+        if (x + 4 < pw) *reinterpret_cast<uint32_t*>(out + 4) = o[1];
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_sao_sparse(const Arenas& A, int max_hctb, cudaStream_t stream) {
+  if (!A.n_tiles || max_hctb <= 0) return cudaSuccess;
+  sao_sparse_kernel<<<A.n_tiles * (uint32_t)max_hctb, 128, 0, stream>>>(A, (uint32_t)max_hctb);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_sao(const Arenas& A, uint32_t max_pitch, uint32_t max_h, cudaStream_t stream) {
   if (!A.n_tiles) return cudaSuccess;

@@ -298,6 +298,9 @@ typedef struct heic_b200_batch heic_b200_batch;
  * and allocates all intermediate and output buffers on the device. */
 int32_t heic_b200_batch_create(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs,
                                heic_b200_batch** out);
+/* The same with apply_transforms != 0: the RGB output of every image is rotated by its irot (as heic_b200_decode_grids does). */
+int32_t heic_b200_batch_create_ex(heic_b200_ctx* ctx, const heic_image_desc* imgs, uint32_t n_imgs, int32_t apply_transforms,
+                                  heic_b200_batch** out);
 void    heic_b200_batch_destroy(heic_b200_batch* b);
 /* Runs slice data -> RGB for the whole batch on the context's stream; does not synchronise. */
 int32_t heic_b200_batch_decode(heic_b200_batch* b);

@@ -435,6 +435,9 @@ extern "C" {
     pub fn heic_b200_batch_create(
         ctx: *mut heic_b200_ctx, imgs: *const heic_image_desc, n_imgs: u32, out: *mut *mut heic_b200_batch,
     ) -> i32;
+    pub fn heic_b200_batch_create_ex(
+        ctx: *mut heic_b200_ctx, imgs: *const heic_image_desc, n_imgs: u32, apply_transforms: i32, out: *mut *mut heic_b200_batch,
+    ) -> i32;
     pub fn heic_b200_batch_destroy(b: *mut heic_b200_batch);
     pub fn heic_b200_batch_decode(b: *mut heic_b200_batch) -> i32;
     pub fn heic_b200_batch_run_stages(b: *mut heic_b200_batch, stage_mask: u32) -> i32;

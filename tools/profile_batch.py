@@ -27,7 +27,7 @@ dec = H.HeicDecoder(0)
 b = dec.batch(images)
 try:
     print("groups:", check_groups_distinct(b, ids.reshape(-1)), flush=True)
-except SystemExit as e:  # e.g. HEIC_B200_CABAC_DEAL=1: measured anyway, but said
+except SystemExit as e:  # e.g. HEIC_B200_CABAC_PLAIN_SORT=1: measured anyway, but said
     print("groups:", e, flush=True)
 s = torch.cuda.ExternalStream(b.stream)
 for _ in range(args.decodes):
