@@ -321,6 +321,8 @@ class HeicDecoder:
         images = list(images)
         arr = _desc_array(images)
         w, h = _canvas(images[0], apply_transforms)
+        if any(_canvas(im, apply_transforms) != (w, h) for im in images[1:]):
+            raise ValueError("decode_grids packs the images into one (n, H, W, 3) array: all canvases (after rotation) must be equal")
         if out is None:
             out = np.empty((len(images), h, w, 3), np.uint8)
         n_tiles = sum(im.n_tiles for im in images)

@@ -213,27 +213,51 @@ __global__ void __launch_bounds__(kColorThreads) color_rotate_kernel(ColorJob J,
     const bool two_rows = ly + 1 < h_v;
     uint32_t w[2][12];
     convert_block<FULL, FUSED>(J, K, image, x0 + lx, y0 + ly, y0 + ly + 1 < J.out_h, w);
-#pragma unroll
-    for (int r = 0; r < 2; r++) {
-      if (r == 1 && !two_rows) break;
-      const uint32_t sy = ly + r;
+    // byte b (0..47) of row r's 48 bytes of RGB
+#define HEIC_RGB_BYTE(r, b) ((w[r][(b) >> 2] >> (8 * ((b) & 3))) & 0xffu)
+    // two such bytes as one 16-bit value (low byte first): one PRMT
+#define HEIC_RGB_PAIR(ra, ba, rb, bb) __byte_perm(w[ra][(ba) >> 2], w[rb][(bb) >> 2], ((ba) & 3) | ((4 + ((bb) & 3)) << 4))
+    if (two_rows && lx + 16 <= w_v && rot != 2 && !(h_v & 1u)) {
+      // quarter turns: the two rows of a column are two neighbouring pixels of one rotated row -- six contiguous bytes at an
+      // even address, written as three 16-bit stores (rot 3: the lower canvas row comes first, rot 1: the upper one)
 #pragma unroll
       for (int i = 0; i < 16; i++) {
         const uint32_t sx = lx + i;
-        if (sx < w_v) {
-          uint32_t row, col;  // position inside the rotated tile
-          if (rot == 1) row = w_v - 1 - sx, col = sy;
-          else if (rot == 2) row = h_v - 1 - sy, col = w_v - 1 - sx;
-          else row = sx, col = h_v - 1 - sy;
-          uint8_t* o = tile + row * kRotRowBytes + col * 3;
+        uint8_t* o = rot == 1 ? tile + (w_v - 1 - sx) * kRotRowBytes + ly * 3 : tile + sx * kRotRowBytes + (h_v - 2 - ly) * 3;
+        uint16_t* o16 = reinterpret_cast<uint16_t*>(o);
+        if (rot == 1) {
+          o16[0] = (uint16_t)HEIC_RGB_PAIR(0, 3 * i, 0, 3 * i + 1);
+          o16[1] = (uint16_t)HEIC_RGB_PAIR(0, 3 * i + 2, 1, 3 * i);
+          o16[2] = (uint16_t)HEIC_RGB_PAIR(1, 3 * i + 1, 1, 3 * i + 2);
+        } else {
+          o16[0] = (uint16_t)HEIC_RGB_PAIR(1, 3 * i, 1, 3 * i + 1);
+          o16[1] = (uint16_t)HEIC_RGB_PAIR(1, 3 * i + 2, 0, 3 * i);
+          o16[2] = (uint16_t)HEIC_RGB_PAIR(0, 3 * i + 1, 0, 3 * i + 2);
+        }
+      }
+    } else {
 #pragma unroll
-          for (int ch = 0; ch < 3; ch++) {
-            const int bidx = i * 3 + ch;
-            o[ch] = (uint8_t)(w[r][bidx >> 2] >> (8 * (bidx & 3)));
+      for (int r = 0; r < 2; r++) {
+        if (r == 1 && !two_rows) break;
+        const uint32_t sy = ly + r;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const uint32_t sx = lx + i;
+          if (sx < w_v) {
+            uint32_t row, col;  // position inside the rotated tile
+            if (rot == 1) row = w_v - 1 - sx, col = sy;
+            else if (rot == 2) row = h_v - 1 - sy, col = w_v - 1 - sx;
+            else row = sx, col = h_v - 1 - sy;
+            uint8_t* o = tile + row * kRotRowBytes + col * 3;
+            o[0] = (uint8_t)HEIC_RGB_BYTE(r, 3 * i);
+            o[1] = (uint8_t)HEIC_RGB_BYTE(r, 3 * i + 1);
+            o[2] = (uint8_t)HEIC_RGB_BYTE(r, 3 * i + 2);
           }
         }
       }
     }
+#undef HEIC_RGB_BYTE
+#undef HEIC_RGB_PAIR
   }
   __syncthreads();
   // rotated tile -> HBM

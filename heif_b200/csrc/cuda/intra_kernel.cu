@@ -56,61 +56,81 @@ __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
 }
 
+// ---- 8.4.4.2.2 reference availability (6.4.1) for a single-slice all-intra picture in z-scan order ---------
+// The left column and the top row exist whenever the block is not on the picture border.  The below-left and
+// above-right N samples belong to ONE aligned N x N block each, which is either completely reconstructed or not
+// started (transform units are atomic in z-order), further cut by the picture limits to a prefix.  So the
+// available samples form one interval [lo, hi] of the scan (bottom-left -> corner -> top-right, positions 0 .. 4N), and
+// the substitution process ("nearest available sample before, else first one after") is a clamp of s to that interval.
+// Reconstructed-yet is a comparison of z-order indices at granularity N inside the CTB: for the below-left
+// neighbour (cx - 1, cy + 1) the highest differing coordinate bit is ctz(cx) in x (where it is smaller) and
+// ctz(cy + 1) in y (where it is larger), and y wins ties; likewise for the above-right one.  OR-ing the CTB size
+// in makes the left / upper CTB (always there) and the lower / right CTB (never there) fall out of the same test.
+// Returns lo | hi << 8 (lo > hi: nothing available -> 1 << (bitDepth - 1)).  Pure arithmetic on the block's position, so
+// the kernel evaluates it for all transform units of a CTU at once, one lane per unit.
+__device__ __forceinline__ uint32_t block_availability(const Ctu& c, int sub, int bx, int by, int log2) {
+  const int N = 1 << log2;
+  const int units = (c.ctb >> sub) >> log2;  // blocks of this size per CTB side
+  const int cx = bx >> log2, cy = by >> log2;
+  const int X0 = (c.x_ctb >> sub) + bx, Y0 = (c.y_ctb >> sub) + by;
+  const bool left_ok = X0 > 0, top_ok = Y0 > 0;
+  int n_bl = 0, n_tr = 0;
+  if (left_ok && __ffs(cx | units) > __ffs(cy + 1)) n_bl = min(N, max(0, (c.h >> sub) - (Y0 + N)));
+  if (top_ok && __ffs(cy | units) >= __ffs(cx + 1)) n_tr = min(N, max(0, (c.w >> sub) - (X0 + N)));
+  const int lo = left_ok ? N - n_bl : 2 * N + 1;
+  const int hi = top_ok ? 3 * N + n_tr : 2 * N - 1;
+  return (uint32_t)lo | ((uint32_t)hi << 8);
+}
+
 // Predicts and reconstructs the N x N block at (bx, by) (plane samples, CTU-relative) of one plane, or — `pair` — of
 // the two chroma planes together (same geometry and mode; buffers `buf_delta` and residuals `res_delta` apart), which
 // shares the availability logic and the loop overheads between Cb and Cr.  A lane produces four horizontally adjacent
 // samples per step.  Deliberately one compact, size-generic body with a single call site: the kernel is
 // instruction-fetch bound when this code is replicated per size and per component.
+// (lo, hi): the interval of available reference positions, from block_availability().
 __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* buf, int buf_delta, int stride, int bx, int by,
                                               int log2, int mode, bool cbf_a, bool cbf_b, const int16_t* __restrict__ resid,
-                                              int res_delta) {
-  const int N = 1 << log2, sub = pair ? 1 : 0, lane = c.lane;
+                                              int res_delta, int lo, int hi) {
+  const int N = 1 << log2, lane = c.lane;
   const int total = 4 * N, cnt = total + 1;  // positions 0 .. 4N: s < 2N left column bottom-up, s = 2N corner, s > 2N top row
   uint8_t* ref = c.ref;
-  // ---- 8.4.4.2.2 reference availability (6.4.1) for a single-slice all-intra picture in z-scan order ---------
-  // The left column and the top row exist whenever the block is not on the picture border.  The below-left and
-  // above-right N samples belong to ONE aligned N x N block each, which is either completely reconstructed or not
-  // started (transform units are atomic in z-order), further cut by the picture limits to a prefix.  So the
-  // available samples form one interval [lo, hi] of the scan (bottom-left -> corner -> top-right), and the
-  // substitution process ("nearest available sample before, else first one after") is a clamp of s to that interval.
-  // Reconstructed-yet is a comparison of z-order indices at granularity N inside the CTB: for the below-left
-  // neighbour (cx - 1, cy + 1) the highest differing coordinate bit is ctz(cx) in x (where it is smaller) and
-  // ctz(cy + 1) in y (where it is larger), and y wins ties; likewise for the above-right one.  OR-ing the CTB size
-  // in makes the left / upper CTB (always there) and the lower / right CTB (never there) fall out of the same test.
-  int lo, hi;
-  {
-    const int units = (c.ctb >> sub) >> log2;  // blocks of this size per CTB side
-    const int cx = bx >> log2, cy = by >> log2;
-    const int X0 = (c.x_ctb >> sub) + bx, Y0 = (c.y_ctb >> sub) + by;
-    const bool left_ok = X0 > 0, top_ok = Y0 > 0;
-    int n_bl = 0, n_tr = 0;
-    if (left_ok && __ffs(cx | units) > __ffs(cy + 1)) n_bl = min(N, max(0, (c.h >> sub) - (Y0 + N)));
-    if (top_ok && __ffs(cy | units) >= __ffs(cx + 1)) n_tr = min(N, max(0, (c.w >> sub) - (X0 + N)));
-    lo = left_ok ? N - n_bl : 2 * N + 1;
-    hi = top_ok ? 3 * N + n_tr : 2 * N - 1;  // lo > hi: nothing available -> 1 << (bitDepth - 1)
-  }
-  if (log2 == 2 && !pair) {
-    // ---- luma 4x4 (half of all calls): the 17 reference samples live in lanes 0..16 (lane s holds scan position s, so
+  if (log2 == 2) {
+    // ---- 4x4 blocks (most calls): the 17 reference samples live in lanes 0..16 (lane s holds scan position s, so
     // left(i) is lane 8 - i and top(i) lane 8 + i), the 16 samples in lanes 0..15, and shuffles replace the reference
-    // arrays, their loops and two warp barriers.  No smoothing at this size.
+    // arrays, their loops and two warp barriers.  No smoothing at this size.  A chroma pair runs the same shuffles on a
+    // second register (same mode, same geometry); the edge filters of DC / horizontal / vertical are luma only.
     const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
-    int r = 128;
+    int r = 128, r2 = 128;
     if (lane <= 16 && lo <= hi) {
       const int d = min(max(lane, lo), hi) - 8;
-      r = corner[d <= 0 ? -d * stride : d];
+      const int off = d <= 0 ? -d * stride : d;
+      r = corner[off];
+      if (pair) r2 = corner[off + buf_delta];
     }
     const int x = lane & 3, y = (lane >> 2) & 3;
+    const bool luma = !pair;
+    int v, v2 = 0;
     const int L = __shfl_sync(0xffffffffu, r, 7 - y), T = __shfl_sync(0xffffffffu, r, 9 + x);  // left(1 + y), top(1 + x)
-    int v;
+    int L2 = 0, T2 = 0;
+    if (pair) L2 = __shfl_sync(0xffffffffu, r2, 7 - y), T2 = __shfl_sync(0xffffffffu, r2, 9 + x);
     if (mode == 0) {
       const int tr = __shfl_sync(0xffffffffu, r, 13), bl = __shfl_sync(0xffffffffu, r, 3);
       v = ((3 - x) * L + (x + 1) * tr + (3 - y) * T + (y + 1) * bl + 4) >> 3;
+      if (pair) {
+        const int tr2 = __shfl_sync(0xffffffffu, r2, 13), bl2 = __shfl_sync(0xffffffffu, r2, 3);
+        v2 = ((3 - x) * L2 + (x + 1) * tr2 + (3 - y) * T2 + (y + 1) * bl2 + 4) >> 3;
+      }
     } else if (mode == 1) {
       const bool in_sum = (lane >= 4 && lane <= 7) || (lane >= 9 && lane <= 12);
-      const int dc = ((int)__reduce_add_sync(0xffffffffu, in_sum ? (unsigned)r : 0u) + 4) >> 3;
+      // both sums in one reduction (each < 2^11)
+      const unsigned sums = __reduce_add_sync(0xffffffffu, in_sum ? (unsigned)r | ((unsigned)r2 << 16) : 0u);
+      const int dc = ((int)(sums & 0xffffu) + 4) >> 3;
       v = dc;
-      if (y == 0) v = x == 0 ? (L + 2 * dc + T + 2) >> 2 : (T + 3 * dc + 2) >> 2;
-      else if (x == 0) v = (L + 3 * dc + 2) >> 2;
+      v2 = ((int)(sums >> 16) + 4) >> 3;
+      if (luma) {
+        if (y == 0) v = x == 0 ? (L + 2 * dc + T + 2) >> 2 : (T + 3 * dc + 2) >> 2;
+        else if (x == 0) v = (L + 3 * dc + 2) >> 2;
+      }
     } else {
       const int angle = kIntraPredAngle[mode];
       const bool vertical = mode >= 18;
@@ -125,15 +145,23 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
       }
       const int a = __shfl_sync(0xffffffffu, r, la), b = __shfl_sync(0xffffffffu, r, lb);  // b unused when fact == 0
       v = ((32 - fact) * a + fact * b + 16) >> 5;
-      if (mode == 26 || mode == 10) {
+      if (pair) {
+        const int a2 = __shfl_sync(0xffffffffu, r2, la), b2 = __shfl_sync(0xffffffffu, r2, lb);
+        v2 = ((32 - fact) * a2 + fact * b2 + 16) >> 5;
+      } else if (mode == 26 || mode == 10) {
         const int c0 = __shfl_sync(0xffffffffu, r, 8), t1s = __shfl_sync(0xffffffffu, r, 9), l1s = __shfl_sync(0xffffffffu, r, 7);
         if (mode == 26 && x == 0) v = clip8(t1s + ((L - c0) >> 1));
         if (mode == 10 && y == 0) v = clip8(l1s + ((T - c0) >> 1));
       }
     }
     if (lane < 16) {
+      uint8_t* o = buf + (by + 1 + y) * stride + bx + 16 + x;
       if (cbf_a) v = clip8(v + (int)resid[lane]);
-      buf[(by + 1 + y) * stride + bx + 16 + x] = (uint8_t)v;
+      o[0] = (uint8_t)v;
+      if (pair) {
+        if (cbf_b) v2 = clip8(v2 + (int)resid[res_delta + lane]);
+        o[buf_delta] = (uint8_t)v2;
+      }
     }
     __syncwarp();
     return;
@@ -419,29 +447,50 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
         }
       }
       // ---- transform units of this CTB in z-order -----------------------------------------------------
-      int idx = 0;
-      while (idx < n4sq) {
-        const uint32_t w = c.tuw[idx];
-        if (!(w & TU_ORIGIN)) {  // quadrant outside the picture
-          idx++;
-          continue;
-        }
-        const int log2 = (int)tu_log2(w), n = 1 << log2;
-        const int ux = (int)compact1((uint32_t)idx), uy = (int)compact1((uint32_t)idx >> 1);
-        const int bx = ux << 2, by = uy << 2;
-        // luma, then (when this TU carries them) Cb and Cr as a pair: one call site keeps the kernel's code small
-        const int n_calls = ((w & TU_HAS_CHROMA) && n_planes == 3) ? 2 : 1;
+      // Everything about a transform unit that is arithmetic on its tu_map word and position (block coordinates, modes,
+      // cbfs, the availability intervals of its luma block and of its chroma pair) is worked out for 32 units at a time,
+      // one lane per 4x4 unit; the sequential walk below then only fetches three words per unit with shuffles.
+      {
         const int buf_delta = (int)(c.buf[2] - c.buf[1]), res_delta = (int)(c.res[2] - c.res[1]);
 #pragma unroll 1
-        for (int k = 0; k < n_calls; k++) {
-          const bool pr = k != 0;
-          predict_block(c, pr, pr ? c.buf[1] : c.buf[0], pr ? buf_delta : 0, pr ? c.stride[1] : c.stride[0],
-                        pr ? (log2 > 2 ? bx : bx - 4) >> 1 : bx, pr ? (log2 > 2 ? by : by - 4) >> 1 : by,
-                        pr ? (log2 > 2 ? log2 - 1 : 2) : log2, pr ? (int)tu_chroma_mode(w) : (int)tu_luma_mode(w),
-                        (w & (pr ? TU_CBF_CB : TU_CBF_Y)) != 0, pr && (w & TU_CBF_CR) != 0,
-                        pr ? c.res[1] + (idx >> 2) * 16 : c.res[0] + idx * 16, pr ? res_delta : 0);
+        for (int base = 0; base < n4sq; base += 32) {
+          const int idx_l = base + lane;
+          const uint32_t wl = idx_l < n4sq ? c.tuw[idx_l] : 0u;
+          uint32_t pa = 0, pb = 0, pc = 0;
+          if (wl & TU_ORIGIN) {
+            const int lg = (int)tu_log2(wl);
+            const int bxl = (int)compact1((uint32_t)idx_l) << 2, byl = (int)compact1((uint32_t)idx_l >> 1) << 2;
+            pa = (uint32_t)bxl | ((uint32_t)byl << 6) | ((uint32_t)lg << 12) | (tu_luma_mode(wl) << 15) | ((wl & TU_CBF_Y) ? 1u << 21 : 0u);
+            pb = block_availability(c, 0, bxl, byl, lg);
+            if ((wl & TU_HAS_CHROMA) && n_planes == 3) {
+              const int lgc = lg > 2 ? lg - 1 : 2;
+              const int bxc = (lg > 2 ? bxl : bxl - 4) >> 1, byc = (lg > 2 ? byl : byl - 4) >> 1;
+              pa |= (1u << 22) | ((wl & TU_CBF_CB) ? 1u << 23 : 0u) | ((wl & TU_CBF_CR) ? 1u << 24 : 0u);
+              pb |= block_availability(c, 1, bxc, byc, lgc) << 16;
+              pc = tu_chroma_mode(wl) | ((uint32_t)bxc << 6) | ((uint32_t)byc << 12) | ((uint32_t)lgc << 18);
+            }
+          }
+          uint32_t todo = __ballot_sync(0xffffffffu, (wl & TU_ORIGIN) != 0);
+          while (todo) {  // warp-uniform
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t a = __shfl_sync(0xffffffffu, pa, src), b = __shfl_sync(0xffffffffu, pb, src);
+            const uint32_t cc = __shfl_sync(0xffffffffu, pc, src);
+            const int idx = base + src;
+            // luma, then (when this unit carries them) Cb and Cr as a pair: ONE call site keeps the kernel's code small
+            const int n_calls = (int)((a >> 22) & 1u) + 1;
+#pragma unroll 1
+            for (int k = 0; k < n_calls; k++) {
+              const bool pr = k != 0;
+              const uint32_t geo = pr ? cc >> 6 : a;        // bx | by << 6 | log2 << 12
+              const uint32_t av = pr ? b >> 16 : b;         // lo | hi << 8
+              predict_block(c, pr, pr ? c.buf[1] : c.buf[0], pr ? buf_delta : 0, pr ? c.stride[1] : c.stride[0], (int)(geo & 63u),
+                            (int)((geo >> 6) & 63u), (int)((geo >> 12) & 7u), (int)((pr ? cc : a >> 15) & 63u), ((a >> (pr ? 23 : 21)) & 1u) != 0,
+                            pr && ((a >> 24) & 1u), pr ? c.res[1] + (idx >> 2) * 16 : c.res[0] + idx * 16, pr ? res_delta : 0,
+                            (int)(av & 0xffu), (int)((av >> 8) & 0xffu));
+            }
+          }
         }
-        idx += (n >> 2) * (n >> 2);
       }
       // ---- CTU -> HBM, 4 bytes per lane, rows of the CTU contiguous across lanes -------------------------
 #pragma unroll

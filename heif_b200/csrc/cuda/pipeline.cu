@@ -915,14 +915,15 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
   // path, ~100 ms for a 70 KB slice), so a chunk only uses the machine when it brings about as many groups as CTAs are
   // resident (444 groups = 296 images of 48 tiles): measured on B200, eight 32-image chunks in flight decode at 10.4 K MP/s,
   // one 256-image chunk per call, double-buffered, at the speed of a resident 256-image batch.  So by default a call is cut
-  // into equal chunks of at most 296 images, and two or three such chunks rotate (the next call's kernels run while this
-  // call's RGB travels to the host); HEIC_B200_PIPE_CHUNK / _SLOTS override.
+  // into equal chunks of at most 296 images, and three such chunks rotate: one in its kernels, one in its D2H copy and one
+  // being staged by the host (with two, the GPU idled while the host staged the next chunk behind a finished copy);
+  // HEIC_B200_PIPE_CHUNK / _SLOTS override.
   uint32_t chunk = (uint32_t)std::max(0, ctx->pipe_chunk);
   if (chunk == 0) {
     const uint32_t parts = (n_imgs + 295u) / 296u;
     chunk = (n_imgs + parts - 1) / parts;
   }
-  const uint32_t n_slots_use = ctx->pipe_slots > 0 ? (uint32_t)ctx->pipe_slots : std::min(8u, std::max(2u, 600u / chunk));
+  const uint32_t n_slots_use = ctx->pipe_slots > 0 ? (uint32_t)ctx->pipe_slots : std::min(8u, std::max(3u, 900u / chunk));
   std::vector<uint32_t> chunk_start;
   for (uint32_t i = 0; i < n_imgs; i += chunk) chunk_start.push_back(i);
   chunk_start.push_back(n_imgs);

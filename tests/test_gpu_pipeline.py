@@ -281,3 +281,45 @@ def test_corrupt_tiles_in_a_multi_group_batch(decoder, heic_file, oracle_rgb):
             y0, x0 = r * 512, c * 512
             assert np.array_equal(out[i, y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)],
                                   oracle_rgb[y0:min(y0 + 512, 3024), x0:min(x0 + 512, 4032)]), (i, t)
+
+
+@pytest.mark.gpu
+def test_output_layout_is_validated_before_anything_is_queued(decoder, heic_file):
+    """image i goes to rgb_out + i * image_stride, so every image must fit its slot -- checked for all images
+    up front (a later, taller image used to let the D2H copy run past its slot)."""
+    import ctypes as C
+
+    from heif_b200 import _capi as K
+
+    img = heic_file.primary
+    aux = heic_file.aux_images[0]  # 2016 x 1512: a different canvas than the primary's 4032 x 3024
+    arr = (K.ImageDesc * 2)()
+    C.memmove(C.byref(arr, 0), C.byref(aux), C.sizeof(K.ImageDesc))
+    C.memmove(C.byref(arr, C.sizeof(K.ImageDesc)), C.byref(img), C.sizeof(K.ImageDesc))
+    pitch = 4032 * 3
+    out = np.zeros((2, 3024, pitch), np.uint8)
+    lib = K.load()
+    # slots sized for the small image: the second image does not fit -> rejected, nothing written
+    rc = lib.heic_b200_decode_grids(decoder._h, arr, 2, out.ctypes.data, pitch, 1512 * pitch, 0, None)
+    assert rc == K.HEIC_E_INVALID_ARG and not out.any()
+    # a pitch too small for the second image is caught before the first image is queued
+    rc = lib.heic_b200_decode_grids(decoder._h, arr, 2, out.ctypes.data, 2016 * 3, out.strides[0], 0, None)
+    assert rc == K.HEIC_E_INVALID_ARG and not out.any()
+    rc = lib.heic_b200_decode_grids(decoder._h, arr, 2, out.ctypes.data, pitch, out.strides[0], 0, None)
+    assert rc == 0 and out[0].any() and out[1].any()
+    with pytest.raises(ValueError):
+        decoder.decode_grids([aux, img])
+
+
+@pytest.mark.gpu
+def test_two_devices_in_one_process(built, heic_file, oracle_rgb):
+    """the shared-memory opt-ins are per device; a second context on another GPU must decode (67 KB intra CTAs)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import heif_b200
+
+    with heif_b200.HeicDecoder(device=0) as d0, heif_b200.HeicDecoder(device=1) as d1:
+        assert np.array_equal(d0.decode(heic_file), oracle_rgb)
+        assert np.array_equal(d1.decode(heic_file), oracle_rgb)
