@@ -317,7 +317,7 @@ static __device__ __noinline__ EngRet eng_gt1_run(Engine e, uint32_t ctx_addr, u
   }
   EngRet r;
   r.e = e;
-  r.v = g1;
+  r.v = g1 | (m << 16);  // m: the significant coefficients past the first eight (they carry no greater1 flag)
   r.bad = greater1_ctx | ((last + 1) << 8);
   return r;
 }
@@ -701,7 +701,7 @@ HEIC_NO_UNROLL
     if (!first_sub_block && greater1_ctx == 0) ctx_set++;
     first_sub_block = 0;
     greater1_ctx = 1;
-    uint32_t g1 = 0;
+    uint32_t g1 = 0, beyond8 = 0;
     int last_g1_pos = -1;
     const int last_sig = 31 - HEIC_CLZ(sig);
     const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
@@ -709,7 +709,8 @@ HEIC_NO_UNROLL
     {
       const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0);
       e = r.e;
-      g1 = r.v;
+      g1 = r.v & 0xffffu;
+      beyond8 = r.v >> 16;
       greater1_ctx = r.bad & 0xff;
       last_g1_pos = (r.bad >> 8) - 1;
     }
@@ -730,6 +731,7 @@ HEIC_NO_UNROLL
           greater1_ctx++;
         }
       }
+      beyond8 = m;
     }
 #endif
     const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
@@ -739,20 +741,26 @@ HEIC_NO_UNROLL
     // read them in one go, most significant bit = first coefficient
     const int n_sign = HEIC_POPC(sig) - (sign_hidden ? 1 : 0);
     uint32_t sign_bits = n_sign ? fl_bypass(n_sign) << (32 - n_sign) : 0u;
-    int num_sig = 0, sum_abs = 0, rice = 0;
+    // baseLevel = 1 + greater1 + greater2, and which coefficients carry a coeff_abs_level_remaining (9.3.3.11 / 7.3.8.11:
+    // baseLevel == ((numSigCoeff < 8) ? ((i == firstG1) ? 3 : 2) : 1)) as bit masks, worked out once per sub-block: among the
+    // first eight that is "greater1 set" -- for the one coefficient that also has a greater2 flag "greater2 set" -- and
+    // every coefficient after the first eight.
+    const uint32_t first_g1 = last_g1_pos >= 0 ? 1u << last_g1_pos : 0u;
+    const uint32_t g2x = g2 ? first_g1 : 0u;
+    const uint32_t need_rem = (g1 & ~first_g1) | g2x | beyond8;
+    int sum_abs = 0, rice = 0;
     uint32_t m = sig;
     while (m) {
       int k = 31 - HEIC_CLZ(m);
       m &= ~(1u << k);
-      int base = 1 + (int)((g1 >> k) & 1u) + ((k == last_g1_pos) ? g2 : 0);
-      int abs_level = base;
-      if (base == ((num_sig < 8) ? ((k == last_g1_pos) ? 3 : 2) : 1)) {
+      int abs_level = 1 + (int)((g1 >> k) & 1u) + (int)((g2x >> k) & 1u);
+      if ((need_rem >> k) & 1u) {
         uint32_t rem = coeff_abs_level_remaining(rice);
         if (rem > 32768u) {
           fail(-3);
           return;
         }
-        abs_level = base + (int)rem;
+        abs_level += (int)rem;
         if (abs_level > 3 * (1 << rice)) rice = rice < 4 ? rice + 1 : 4;  // decoder.rs:230-236
       }
       int v = (sign_bits >> 31) ? -abs_level : abs_level;
@@ -764,7 +772,6 @@ HEIC_NO_UNROLL
       uint32_t pxy = scan_xy(scan_idx, 2, k);
       int xc = (xs << 2) + (int)(pxy & 15u), yc = (ys << 2) + (int)(pxy >> 4);
       out[yc * n + xc] = (int16_t)clip3i(-32768, 32767, v);
-      num_sig++;
     }
   }
   HEIC_HD int residual_coding(int log2, int c_idx, int pred_mode, int16_t* out) {
