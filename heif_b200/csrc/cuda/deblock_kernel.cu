@@ -41,39 +41,83 @@ struct Pic {
   int w8, log2_ctb, wctb;
 };
 
-// log2 size of the transform unit covering luma sample (x, y): probe the four aligned candidate origins.  The probes
-// are independent loads (no early exit), so they — and those of the cell's other edge segments — are in flight together.
-__device__ __forceinline__ int tu_log2_at(const Pic& p, int x, int y) {
+// Is the edge through luma sample (x, y) at coordinate `pos` (x for a vertical edge, y for a horizontal one; a multiple
+// of 8) a transform-block edge?  Transform units of 4x4 and 8x8 always end on the 8-sample grid, and nothing is larger than
+// 32x32, so the edge is NOT one only if a 16x16 or 32x32 unit covers the sample and `pos` is not a multiple of its size: at
+// most two probes of tu_map (the 16- and the 32-aligned candidate origins), none on the 32-sample grid (CTB borders included).
+__device__ __forceinline__ bool is_tu_edge(const Pic& p, int x, int y, int pos) {
+#if defined(HEIC_DEBLOCK_PROBE_UNCONDITIONAL)
+  // A/B variant: both probes always issued (independent loads, no branch on the position)
+  {
+    const int ctb4 = 1 << (p.log2_ctb - 2);
+    const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
+    const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
+    const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
+    const uint32_t w3 = tu[z & ~63u], w2 = tu[z & ~15u];
+    const bool in32 = (w3 & 7u) == (TU_ORIGIN | (3u << 1)) && (pos & 31) != 0;
+    const bool in16 = (w2 & 7u) == (TU_ORIGIN | (2u << 1)) && (pos & 15) != 0;
+    return !(in32 || in16);
+  }
+#endif
+  if ((pos & 31) == 0) return true;
   const int ctb4 = 1 << (p.log2_ctb - 2);
   const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
   const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
   const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
-  const uint32_t w0 = tu[z], w1 = tu[z & ~3u], w2 = tu[z & ~15u], w3 = tu[z & ~63u];
-  int lg = 5;  // a fully parsed picture always matches one of the four
-  if ((w3 & 7u) == (TU_ORIGIN | (3u << 1))) lg = 5;
-  if ((w2 & 7u) == (TU_ORIGIN | (2u << 1))) lg = 4;
-  if ((w1 & 7u) == (TU_ORIGIN | (1u << 1))) lg = 3;
-  if ((w0 & 7u) == (TU_ORIGIN | (0u << 1))) lg = 2;
-  return lg;
+  const uint32_t w3 = tu[z & ~63u];
+  bool inside = (w3 & 7u) == (TU_ORIGIN | (3u << 1));
+  if (pos & 15) {
+    const uint32_t w2 = tu[z & ~15u];
+    inside = inside || (w2 & 7u) == (TU_ORIGIN | (2u << 1));
+  }
+  return !inside;
 }
 __device__ __forceinline__ int qp_at(const Pic& p, int x, int y) { return p.qp_map[(y >> 3) * p.w8 + (x >> 3)]; }
 
-// Luma edge filter over one 4-line segment held in registers: P(i, l) / Q(i, l) are references.
-// s[l][0..7] = p3 p2 p1 p0 q0 q1 q2 q3 of line l.
-__device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_sum, int beta_off2, int tc_off2) {
+// ---- the cell stays PACKED (rw[r][0] = samples 0..3 of row r, rw[r][1] = samples 4..7) and only the lines an edge
+// segment really filters are unpacked: a segment that is no transform-block edge, or whose decisions (taken on its first
+// and last line, 8.7.2.5.3) say "leave it", costs no unpacking and no repacking, and the unpacked cell (64 registers) never
+// exists.  Line l of a vertical-edge segment s is row 4s + l (p3..p0 = left word, q0..q3 = right word); line l of a
+// horizontal-edge segment s is column 4s + l (byte l of word s of rows 0..7).
+template <bool VERT>
+__device__ __forceinline__ void get_line(const uint32_t (&rw)[8][2], int s, int l, int (&v)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    v[i] = VERT ? (int)((rw[4 * s + l][i >> 2] >> (8 * (i & 3))) & 0xffu) : (int)((rw[i][s] >> (8 * l)) & 0xffu);
+}
+// writes back samples 1..6 of the line (p2 p1 p0 q0 q1 q2: all a filter can change)
+template <bool VERT>
+__device__ __forceinline__ void put_line(uint32_t (&rw)[8][2], int s, int l, const int (&v)[8]) {
+  if (VERT) {
+    rw[4 * s + l][0] = (rw[4 * s + l][0] & 0x000000ffu) | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    rw[4 * s + l][1] = (rw[4 * s + l][1] & 0xff000000u) | (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16);
+  } else {
+#pragma unroll
+    for (int i = 1; i < 7; i++) rw[i][s] = (rw[i][s] & ~(0xffu << (8 * l))) | ((uint32_t)v[i] << (8 * l));
+  }
+}
+
+// 8.7.2.5.3 decisions + 8.7.2.5.7 filters of one luma edge segment.  Returns whether anything changed.
+template <bool VERT>
+__device__ __forceinline__ bool filter_luma_segment(uint32_t (&rw)[8][2], int seg, int qp_sum, int beta_off2, int tc_off2) {
   const int qpl = (qp_sum + 1) >> 1;
   const int beta = kBetaTable[clip3(0, 51, qpl + beta_off2)];
   const int tc = kTcTable[clip3(0, 53, qpl + 2 + tc_off2)];
+  int s[4][8];
+  get_line<VERT>(rw, seg, 0, s[0]);
+  get_line<VERT>(rw, seg, 3, s[3]);
   const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
   const int dq0 = abs(s[0][6] - 2 * s[0][5] + s[0][4]), dq3 = abs(s[3][6] - 2 * s[3][5] + s[3][4]);
   const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
-  if (dpq0 + dpq3 >= beta) return;
+  if (dpq0 + dpq3 >= beta) return false;
   const bool s0 = 2 * dpq0 < (beta >> 2) && abs(s[0][0] - s[0][3]) + abs(s[0][4] - s[0][7]) < (beta >> 3) &&
                   abs(s[0][3] - s[0][4]) < ((5 * tc + 1) >> 1);
   const bool s3 = 2 * dpq3 < (beta >> 2) && abs(s[3][0] - s[3][3]) + abs(s[3][4] - s[3][7]) < (beta >> 3) &&
                   abs(s[3][3] - s[3][4]) < ((5 * tc + 1) >> 1);
   const bool strong = s0 && s3;
   const bool dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
+  get_line<VERT>(rw, seg, 1, s[1]);
+  get_line<VERT>(rw, seg, 2, s[2]);
 #pragma unroll
   for (int l = 0; l < 4; l++) {
     const int p3 = s[l][0], p2 = s[l][1], p1 = s[l][2], p0 = s[l][3];
@@ -95,21 +139,28 @@ __device__ __forceinline__ void filter_luma_segment(int (&s)[4][8], int qp_sum, 
         if (deq) s[l][5] = clip8(q1 + clip3(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
       }
     }
+    put_line<VERT>(rw, seg, l, s[l]);
   }
+  return true;
 }
 
-__device__ __forceinline__ void filter_chroma_segment(int (&s)[4][8], int qp_sum, int c_qp_off, int tc_off2) {
+template <bool VERT>
+__device__ __forceinline__ bool filter_chroma_segment(uint32_t (&rw)[8][2], int seg, int qp_sum, int c_qp_off, int tc_off2) {
   const int qpi = ((qp_sum + 1) >> 1) + c_qp_off;  // cQpPicOffset: PPS offset only (8.7.2.5.5)
   const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
   const int tc = kTcTable[clip3(0, 53, qpc + 2 + tc_off2)];
-  if (!tc) return;
+  if (!tc) return false;
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    const int p1 = s[l][2], p0 = s[l][3], q0 = s[l][4], q1 = s[l][5];
+    int v[8];
+    get_line<VERT>(rw, seg, l, v);
+    const int p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5];
     const int delta = clip3(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
-    s[l][3] = clip8(p0 + delta);
-    s[l][4] = clip8(q0 - delta);
+    v[3] = clip8(p0 + delta);
+    v[4] = clip8(q0 - delta);
+    put_line<VERT>(rw, seg, l, v);
   }
+  return true;
 }
 
 // One shifted cell of plane CIDX.  (k, j): cell indices; the cell covers plane samples
@@ -120,21 +171,16 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
   constexpr int SUB = CIDX ? 1 : 0;
   const int x0 = 8 * k - 4, y0 = 8 * j - 4;
   const bool has_left = k > 0, has_right = 8 * k < pw, has_top = j > 0, has_bottom = 8 * j < ph;
-  int px[8][8];
+  uint32_t rw[8][2];
   // rows y0 .. y0+7; the left half [x0, x0+4) exists when k > 0, the right half when 8k < pw
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const bool row_ok = r < 4 ? has_top : has_bottom;
-    uint32_t a = 0, b = 0;
+    rw[r][0] = rw[r][1] = 0;
     if (row_ok) {
       const uint8_t* row = plane + (size_t)(y0 + r) * pitch;
-      if (has_left) a = *reinterpret_cast<const uint32_t*>(row + x0);
-      if (has_right) b = *reinterpret_cast<const uint32_t*>(row + x0 + 4);
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      px[r][i] = (int)((a >> (8 * i)) & 0xffu);
-      px[r][4 + i] = (int)((b >> (8 * i)) & 0xffu);
+      if (has_left) rw[r][0] = *reinterpret_cast<const uint32_t*>(row + x0);
+      if (has_right) rw[r][1] = *reinterpret_cast<const uint32_t*>(row + x0 + 4);
     }
   }
   // ---- which of the cell's four edge segments exist, and their QPs: all metadata loads issued before any filtering ----
@@ -147,73 +193,44 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
   for (int g = 0; g < 4; g++) {
     const bool vert = g < 2;
     const int half = g & 1;
-    bool ok = has_left && has_right && has_top && has_bottom;
+    bool ok;
     if (vert) ok = has_left && has_right && (half == 0 ? has_top : has_bottom);
     else ok = has_top && has_bottom && (half == 0 ? has_left : has_right);
     const int xl = vert ? xe : (x0 + 4 * half) << SUB, yl = vert ? (y0 + 4 * half) << SUB : ye;
     seg_do[g] = false;
     seg_qp[g] = 0;
     if (ok) {
-      const int lg = tu_log2_at(pic, xl, yl);
       seg_qp[g] = qp_at(pic, xl, yl) + (vert ? qp_at(pic, xl - 1, yl) : qp_at(pic, xl, yl - 1));
-      seg_do[g] = ((vert ? xl : yl) & ((1 << lg) - 1)) == 0;  // a transform-block edge
+      seg_do[g] = is_tu_edge(pic, xl, yl, vert ? xl : yl);
     }
   }
   bool changed = false;
+  // vertical edge first, then the horizontal edge on the vertically filtered samples (the order 8.7.2 prescribes)
 #pragma unroll
-  for (int seg = 0; seg < 2; seg++) {
-    if (!seg_do[seg]) continue;
-    int s[4][8];
+  for (int seg = 0; seg < 2; seg++)
+    if (seg_do[seg])
+      changed |= CIDX == 0 ? filter_luma_segment<true>(rw, seg, seg_qp[seg], beta_off2, tc_off2)
+                           : filter_chroma_segment<true>(rw, seg, seg_qp[seg], c_qp_off, tc_off2);
 #pragma unroll
-    for (int l = 0; l < 4; l++)
-#pragma unroll
-      for (int i = 0; i < 8; i++) s[l][i] = px[4 * seg + l][i];
-    if (CIDX == 0) filter_luma_segment(s, seg_qp[seg], beta_off2, tc_off2);
-    else filter_chroma_segment(s, seg_qp[seg], c_qp_off, tc_off2);
-#pragma unroll
-    for (int l = 0; l < 4; l++)
-#pragma unroll
-      for (int i = 0; i < 8; i++) px[4 * seg + l][i] = s[l][i];
-    changed = true;
-  }
-  // ---- horizontal edge on the vertically filtered samples ----------------------------------
-#pragma unroll
-  for (int seg = 0; seg < 2; seg++) {
-    if (!seg_do[2 + seg]) continue;
-    int s[4][8];
-#pragma unroll
-    for (int l = 0; l < 4; l++)
-#pragma unroll
-      for (int i = 0; i < 8; i++) s[l][i] = px[i][4 * seg + l];
-    if (CIDX == 0) filter_luma_segment(s, seg_qp[2 + seg], beta_off2, tc_off2);
-    else filter_chroma_segment(s, seg_qp[2 + seg], c_qp_off, tc_off2);
-#pragma unroll
-    for (int l = 0; l < 4; l++)
-#pragma unroll
-      for (int i = 0; i < 8; i++) px[i][4 * seg + l] = s[l][i];
-    changed = true;
-  }
+  for (int seg = 0; seg < 2; seg++)
+    if (seg_do[2 + seg])
+      changed |= CIDX == 0 ? filter_luma_segment<false>(rw, seg, seg_qp[2 + seg], beta_off2, tc_off2)
+                           : filter_chroma_segment<false>(rw, seg, seg_qp[2 + seg], c_qp_off, tc_off2);
   if (!changed) return;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const bool row_ok = r < 4 ? has_top : has_bottom;
     if (!row_ok) continue;
     uint8_t* row = plane + (size_t)(y0 + r) * pitch;
-    uint32_t a = 0, b = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      a |= (uint32_t)px[r][i] << (8 * i);
-      b |= (uint32_t)px[r][4 + i] << (8 * i);
-    }
-    if (has_left) *reinterpret_cast<uint32_t*>(row + x0) = a;
-    if (has_right) *reinterpret_cast<uint32_t*>(row + x0 + 4) = b;
+    if (has_left) *reinterpret_cast<uint32_t*>(row + x0) = rw[r][0];
+    if (has_right) *reinterpret_cast<uint32_t*>(row + x0 + 4) = rw[r][1];
   }
 }
 
 // One launch for luma (KIND 0) and one for the two chroma planes (KIND 1): each launch then runs a single filter body
 // that fits the instruction cache.  grid: flat over (tile, block of cells of the tile), cells numbered row by row.
 #ifndef HEIC_DEBLOCK_MIN_CTAS
-#define HEIC_DEBLOCK_MIN_CTAS 6
+#define HEIC_DEBLOCK_MIN_CTAS 8
 #endif
 template <int KIND>
 __global__ void __launch_bounds__(128, HEIC_DEBLOCK_MIN_CTAS) deblock_kernel(Arenas A, uint32_t blocks_per_tile) {

@@ -19,9 +19,9 @@ namespace dev {
 
 namespace {
 
-__device__ const int8_t kIntraPredAngle[35] = {0,   0,   32,  26,  21,  17, 13, 9,  5,  2,  0,  -2, -5, -9, -13, -17, -21, -26,
+__constant__ int8_t kIntraPredAngle[35] = {0,   0,   32,  26,  21,  17, 13, 9,  5,  2,  0,  -2, -5, -9, -13, -17, -21, -26,
                                                -32, -26, -21, -17, -13, -9, -5, -2, 0,  2,  5,  9,  13, 17, 21,  26,  32};
-__device__ const int16_t kInvAngle[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256,
+__constant__ int16_t kInvAngle[15] = {-4096, -1638, -910, -630, -482, -390, -315, -256,
                                           -315,  -390,  -482, -630, -910, -1638, -4096};  // modes 11..25
 
 __device__ __forceinline__ uint32_t compact1(uint32_t v) {

@@ -94,12 +94,13 @@ constexpr int kWarpsPerCta = 8;
 constexpr int kTmpPerWarp = 32 * 34;  // int16 elements: one 32x32 block with padded rows
 
 // ---- list construction ---------------------------------------------------------------------------------------
-// A CTA classifies kListPerCta consecutive tu_map entries of one tile, four per thread.  The per-class item counts are
+// A CTA classifies kListPerCta consecutive tu_map entries of one tile, sixteen per thread.  The per-class item counts are
 // packed in one 64-bit word (12 bits per class) so a single warp scan places every thread's items; a warp reserves its
 // space in the CTA with shared-memory atomics and the CTA reserves its space in every list with one global atomic per
 // class.  Item order within a list is not deterministic; the blocks are independent, so the results are.
 constexpr int kListThreads = 256;
-constexpr int kListPerCta = 4 * kListThreads;
+constexpr int kListIter = 4;                              // 16-byte loads per thread
+constexpr int kListPerCta = 4 * kListThreads * kListIter;  // tu_map entries per CTA (16 KB)
 
 // classes of the (up to) three coded blocks of a tu_map word, 3 bits each (7: none)
 __device__ __forceinline__ uint32_t classify(uint32_t w, bool chroma) {
@@ -128,21 +129,25 @@ __global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_
   if (threadIdx.x < LIST_CLASSES) cta_cnt[threadIdx.x] = 0;
   __syncthreads();
   const bool chroma = pp->chroma != 0;
-  const uint32_t i0 = first + threadIdx.x * 4;  // n_tu and tu_off are multiples of 16
-  uint4 wv = make_uint4(0u, 0u, 0u, 0u);
-  if (i0 < (uint32_t)pp->n_tu) wv = *reinterpret_cast<const uint4*>(A.tu_map + tp->tu_off + i0);
-  const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
-  uint32_t cls[4];
+  // kListIter coalesced 16-byte loads per thread (n_tu and tu_off are multiples of 16)
+  uint32_t cls[kListIter][4];
   unsigned long long mine = 0;  // items of this thread per class, 12 bits each
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    cls[e] = 0x1ffu;
-    if (w[e]) {
-      cls[e] = classify(w[e], chroma);
+  for (int it = 0; it < kListIter; it++) {
+    const uint32_t i0 = first + (uint32_t)it * (4 * kListThreads) + threadIdx.x * 4;
+    uint4 wv = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 < (uint32_t)pp->n_tu) wv = *reinterpret_cast<const uint4*>(A.tu_map + tp->tu_off + i0);
+    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        const uint32_t k = (cls[e] >> (3 * c)) & 7u;
-        if (k < LIST_CLASSES) mine += 1ull << (12 * k);
+    for (int e = 0; e < 4; e++) {
+      cls[it][e] = 0x1ffu;
+      if (w[e]) {
+        cls[it][e] = classify(w[e], chroma);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const uint32_t k = (cls[it][e] >> (3 * c)) & 7u;
+          if (k < LIST_CLASSES) mine += 1ull << (12 * k);
+        }
       }
     }
   }
@@ -165,17 +170,21 @@ __global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_
   if (!mine) return;
   unsigned long long run = incl - mine;
 #pragma unroll
-  for (int e = 0; e < 4; e++) {
-    if (cls[e] == 0x1ffu) continue;
+  for (int it = 0; it < kListIter; it++) {
+    const uint32_t i0 = first + (uint32_t)it * (4 * kListThreads) + threadIdx.x * 4;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-      const uint32_t k = (cls[e] >> (3 * c)) & 7u;
-      if (k < LIST_CLASSES) {
-        uint2_t v;
-        v.x = tile;
-        v.y = (i0 + e) | ((uint32_t)c << 30);
-        A.tu_list[(size_t)cta_base[k] + warp_base[warp][k] + ((uint32_t)(run >> (12 * k)) & 0xfffu)] = v;
-        run += 1ull << (12 * k);
+    for (int e = 0; e < 4; e++) {
+      if (cls[it][e] == 0x1ffu) continue;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const uint32_t k = (cls[it][e] >> (3 * c)) & 7u;
+        if (k < LIST_CLASSES) {
+          uint2_t v;
+          v.x = tile;
+          v.y = (i0 + e) | ((uint32_t)c << 30);
+          A.tu_list[(size_t)cta_base[k] + warp_base[warp][k] + ((uint32_t)(run >> (12 * k)) & 0xfffu)] = v;
+          run += 1ull << (12 * k);
+        }
       }
     }
   }
@@ -235,9 +244,49 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, 
     int16_t* blk = item.blk;
     if (col == 0) blk_of[warp][k] = blk;
     const bool tskip = active && tu_tskip(item.w, item.cidx);
+    // ---- DC-only blocks (every block of this warp step has at most its DC coefficient; most large blocks of smooth
+    // pictures): both 1-D passes of a lone DC term are a multiplication by 64, so every sample of the block is the same
+    // value -- no butterflies, no transpose tile, just the fill.  Decided on the raw levels, warp-uniformly.
+    int x[N], y[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) x[j] = active ? (int)blk[j * N + col] : 0;  // raw levels of this lane's column
+    {
+      int any_other = 0;
+#pragma unroll
+      for (int j = 0; j < N; j++) any_other |= (j == 0 && col == 0) ? 0 : x[j];
+      if (!__any_sync(0xffffffffu, any_other != 0 || tskip)) {
+        int v = 0;
+        if (active && col == 0) {
+          const int lvl = x[0];
+          const int scale = item_scale(item);
+          int mf = 16;
+          if (item.pp->scaling_enabled) {
+            const ScalingSet* sc = A.scaling + item.pp->scaling_set;
+            mf = N == 8 ? sc->f8[item.cidx][0] : N == 16 ? sc->f16[item.cidx][0] : sc->f32[item.cidx][0];
+          }
+          constexpr int BD_SHIFT = LOG2 + 3;
+          long long p = ((long long)lvl * (mf * scale) + (1ll << (BD_SHIFT - 1))) >> BD_SHIFT;
+          const int dc = (int)min(32767ll, max(-32768ll, p));
+          const int t1 = clip16((64 * dc + 64) >> 7);
+          v = clip16((64 * t1 + 2048) >> 12);
+        }
+        v = __shfl_sync(0xffffffffu, v, k * N);  // the block's lane 0
+        const uint32_t vv = ((uint32_t)v & 0xffffu) * 0x10001u;
+        constexpr int PAIRS = N * N / 2;
+        const uint32_t n_active = min((uint32_t)K, count - step * K);
+#pragma unroll
+        for (int g = 0; g < K; g++) {
+          if ((uint32_t)g >= n_active) break;  // warp-uniform
+          const uint32_t vg = __shfl_sync(0xffffffffu, vv, g * N);
+          uint4* dst = reinterpret_cast<uint4*>(__shfl_sync(0xffffffffu, (unsigned long long)blk, g * N));
+#pragma unroll 4
+          for (int q = lane; q < PAIRS / 4; q += 32) dst[q] = make_uint4(vg, vg, vg, vg);
+        }
+        continue;
+      }
+    }
     // The two 1-D passes run as one loop; for N == 32 it is not unrolled, so the three butterfly variants exist once
     // instead of twice (3.5 K instructions did not fit the instruction cache: stall_no_instruction 5.7 per issue).
-    int x[N], y[N];
     int nz2 = 0;
     constexpr int UNROLL = N == 32 ? 1 : 2;
 #pragma unroll UNROLL
@@ -248,10 +297,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, 
         int nz_rows = 0;
         // raw levels first: only the rows up to the last non-zero one (warp-uniform bound) are scaled afterwards
 #pragma unroll
-        for (int j = 0; j < N; j++) {
-          x[j] = active ? (int)blk[j * N + col] : 0;
-          nz_rows = x[j] ? j + 1 : nz_rows;
-        }
+        for (int j = 0; j < N; j++) nz_rows = x[j] ? j + 1 : nz_rows;
         // extents of the non-zero coefficients, uniform over the warp so the butterfly variant is too
         int nz1 = nz_rows;
 #pragma unroll
