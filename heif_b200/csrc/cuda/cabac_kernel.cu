@@ -23,6 +23,11 @@
 namespace heic {
 namespace dev {
 
+#if !defined(__CUDA_ARCH__)
+// cabac_parse.cuh declares the kernels' dynamic shared memory for the device pass only (the header also builds with g++)
+extern __shared__ __align__(16) unsigned char heic_cabac_smem[];
+#endif
+
 namespace {
 
 constexpr int kMaxRows = 512;
@@ -32,56 +37,73 @@ constexpr int kMaxRows = 512;
 
 struct CtaShared {
   CabacTabs tabs;
+  alignas(16) Arenas arenas;  // at kSmemArenasOff: the parser reaches the tile's buffers through it (Parser::arenas())
   int progress[kMaxRows];  // CTUs finished per CTB row (TILES == 32: by all lanes of the row's warp), plus the
                            // group's base (see cabac_kernel): values only ever grow
   int aborted[32];         // per tile of the CTA: use + 1 of the group in which the tile failed
   unsigned group_slot[4];  // persistent CTAs: group taken for use k in slot k & 3, tagged with the use
 };
 
+static_assert(offsetof(CtaShared, arenas) == kSmemArenasOff, "Parser::arenas() expects the arena pointers right behind the tables");
+constexpr size_t kCtaSharedBytes = (sizeof(CtaShared) + 15) & ~(size_t)15;
+// per-thread cold words of the parser (tile index, QP state): CW_COUNT words, one column per thread that parses
+template <int TILES>
+struct ColdBytes {
+  static constexpr size_t value = (size_t)Parser<TILES>::CW_COUNT * (TILES == 32 ? 1024 : 64);
+};
+
+// The wavefront hand-shake of parse_rows.  Everything it touches is reached from the kernel's shared-memory symbol and
+// the arena pointers kept there -- no pointer members: the structure is live for the whole kernel, and the CABAC kernel
+// is bound by its register file.
 template <int TILES>
 struct SmemSync {
-  volatile int* progress;
-  volatile int* aborted;  // this thread's tile
-  int* status_code;       // global
   static constexpr int kSaveStride = 1;
-  uint8_t* save_base;     // this tile's WPP context snapshots in HBM, NUM_CTX_PAD bytes per CTB row (written once and
-                          // read once per row, so they need not occupy shared memory: that is what bounds occupancy)
-  int lane;
-  int base;               // added to every progress value of the current group (persistent CTAs)
-  int use1;               // current use + 1
+  uint32_t lane, tile;
+  int base;  // added to every progress value of the current group (persistent CTAs)
+  int use1;  // current use + 1
+
+  __device__ __forceinline__ CtaShared* sh() const { return reinterpret_cast<CtaShared*>(heic_cabac_smem); }
+  __device__ __forceinline__ volatile int* progress() const { return sh()->progress; }
+  __device__ __forceinline__ volatile int* aborted() const { return &sh()->aborted[TILES == 1 ? 0 : lane]; }
 
   __device__ __forceinline__ bool wait(int row, int n) {
     unsigned ns = 32;
+    volatile int* pr = progress();
     if (TILES == 1) {
-      while (progress[row] < base + n && *aborted != use1) {
+      while (pr[row] < base + n && *aborted() != use1) {
         __nanosleep(ns);
         if (ns < 2048) ns *= 2;
       }
     } else {
       __syncwarp();
       if (lane == 0)
-        while (progress[row] < base + n) {
+        while (pr[row] < base + n) {
           __nanosleep(ns);
           if (ns < 2048) ns *= 2;
         }
       __syncwarp();
     }
     __threadfence_block();
-    return *aborted != use1;
+    return *aborted() != use1;
   }
   __device__ __forceinline__ void publish(int row, int n) {
     __threadfence_block();
     if (TILES == 1) {
-      progress[row] = base + n;
+      progress()[row] = base + n;
     } else {
       __syncwarp();
-      if (lane == 0) progress[row] = base + n;
+      if (lane == 0) progress()[row] = base + n;
     }
   }
-  __device__ __forceinline__ uint8_t* save_area(int row) { return save_base + (size_t)row * NUM_CTX_PAD; }
+  // this tile's WPP context snapshots in HBM, NUM_CTX_PAD bytes per CTB row (written once and read once per row, so they
+  // need not occupy shared memory: that is what bounds occupancy)
+  __device__ __forceinline__ uint8_t* save_area(int row) {
+    const Arenas& A = sh()->arenas;
+    return A.wpp_save + A.tiles[tile].wpp_off + (size_t)row * NUM_CTX_PAD;
+  }
   __device__ __forceinline__ void abort(int code) {
-    if (code != -100) atomicCAS(status_code, 0, code);
-    *aborted = use1;
+    if (code != -100) atomicCAS(&sh()->arenas.status[tile].code, 0, code);
+    *aborted() = use1;
     __threadfence_block();
   }
 };
@@ -94,7 +116,7 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
                                                     uint32_t* group_counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CtaShared* sh = reinterpret_cast<CtaShared*>(smem_raw);
-  uint8_t* ctx_all = smem_raw + ((sizeof(CtaShared) + 15) & ~(size_t)15);
+  uint8_t* ctx_all = smem_raw + kCtaSharedBytes + ColdBytes<TILES>::value;
 
   {  // tables -> shared memory
     const uint32_t* src = reinterpret_cast<const uint32_t*>(gtabs);
@@ -103,6 +125,7 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
     for (int i = threadIdx.x; i < kMaxRows; i += blockDim.x) sh->progress[i] = 0;
     if (threadIdx.x < 32) sh->aborted[threadIdx.x] = 0;
     if (threadIdx.x < 4) sh->group_slot[threadIdx.x] = 0;
+    if (threadIdx.x == 0) sh->arenas = A;
   }
   __syncthreads();
 
@@ -148,33 +171,20 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   const PicParams* pp = A.pics + tp->pic;
 
   Parser<TILES> P;
-  P.T = &sh->tabs;
-  P.ctx = ctx_all + (size_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0 : lane);
-  P.ctx_off = (uint32_t)(P.ctx - smem_raw);
-  // keep the table offset in a register: left alone, ptxas rematerialises it from %tid (S2R + 6 ALU ops) at every bin
-  asm volatile("" : "+r"(P.ctx_off));
-  P.pp = pp;
-  P.tp = tp;
-  P.tu_map = A.tu_map + tp->tu_off;
-  P.coeff0 = A.coeff + tp->coeff_off[0];
-  P.coeff1 = A.coeff + tp->coeff_off[1];
-  P.coeff2 = A.coeff + tp->coeff_off[2];
-  P.ipm = A.ipm + tp->map4_off;
-  P.ct_depth = A.ct_depth + tp->map8_off;
-  P.qp_map = A.qp_map + tp->map8_off;
-  P.sao = A.sao + tp->sao_off;
+  P.ctx_off = (uint32_t)(kCtaSharedBytes + ColdBytes<TILES>::value) + (uint32_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0u : (uint32_t)lane);
+  P.cold_off = (uint32_t)kCtaSharedBytes + (TILES == 32 ? threadIdx.x * 4u : (uint32_t)slot * 4u);
+  // keep the offsets in registers: left alone, ptxas rematerialises them from %tid (S2R + ALU ops) at every use
+  asm volatile("" : "+r"(P.ctx_off), "+r"(P.cold_off));
+  P.cold(Parser<TILES>::CW_TILE) = (int)tile;
   P.e.data = A.bitstream + tp->bs_off;
   P.err = active ? 0 : -100;
 
   SmemSync<TILES> sync;
-  sync.progress = sh->progress;
-  sync.aborted = &sh->aborted[TILES == 1 ? 0 : lane];
-  sync.status_code = &A.status[tile].code;
-  sync.lane = lane;
+  sync.lane = (uint32_t)lane;
+  sync.tile = tile;
   sync.base = use << 12;
   sync.use1 = use + 1;
-  sync.save_base = A.wpp_save + tp->wpp_off;
-  if (!active) *sync.aborted = use + 1;
+  if (!active) *sync.aborted() = use + 1;
 
   const uint32_t ctus = parse_rows<TILES>(P, A.substreams + tp->sub_first, slot, n_slots, sync);
   if (active) {
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
 }
 
 size_t cabac_smem_bytes(int tiles_per_cta, int n_slots) {
-  return ((sizeof(CtaShared) + 15) & ~(size_t)15) + (size_t)n_slots * NUM_CTX_PAD * tiles_per_cta;
+  return kCtaSharedBytes + (tiles_per_cta == 32 ? ColdBytes<32>::value : ColdBytes<1>::value) + (size_t)n_slots * NUM_CTX_PAD * tiles_per_cta;
 }
 
 cudaError_t launch_cabac(const Arenas& A, const CabacTabs* tabs, const uint32_t* order, uint32_t n_groups,

@@ -40,6 +40,9 @@ struct CabacTabs {
   uint64_t sig_nib[15];
   uint8_t init_value[NUM_CTX_PAD];
 };
+// Layout of the CABAC kernels' dynamic shared memory as far as the parser addresses it: the tables at offset 0, then a copy
+// of the batch's arena pointers (cabac_kernel.cu puts them there; Parser::arenas()).
+constexpr uint32_t kSmemArenasOff = (uint32_t)((sizeof(CabacTabs) + 15) & ~(size_t)15);
 
 #if defined(__CUDA_ARCH__)
 #define HEIC_NO_UNROLL _Pragma("unroll 1")
@@ -376,6 +379,31 @@ HEIC_HD uint8_t context_init_state(int init_value, int slice_qp) {
 template <int STRIDE, class Eng = Engine>
 struct Parser {
   Eng e;
+  // current CU
+  int part_nxn, chroma_mode, cu_x, cu_y, cu_log2;
+  uint32_t pu_modes;  // IntraPredModeY of the (up to) four prediction blocks, 8 bits each (no indexed arrays: they
+                      // would live in local memory)
+  int err;
+  // What is touched once per transform unit or less -- the tile's arena pointers, its parameter structures and the QP
+  // state of 8.6.1 -- is reached through accessors.  On the device it lives in the kernel's shared memory (the tile index
+  // and the QP state in per-thread words, the arena bases once per CTA), NOT in registers: held in registers it cost 28 of
+  // them for the whole kernel, and the register file is what bounds the CABAC kernel's occupancy (4 CTAs per SM at 64
+  // registers against 3 at 80).  On the host (tests/emul, tests/synth, tests/fuzz) they are plain members.
+  enum { CW_TILE = 0, CW_QP_CODED, CW_QP_DELTA, CW_QP_Y, CW_QP_LAST, CW_QP_PRED, CW_QP_FIRST, CW_QG_X, CW_QG_Y, CW_COUNT };
+#if defined(__CUDA_ARCH__)
+  static constexpr uint32_t kColdStride = STRIDE == 32 ? 1024u : 64u;  // bytes between a thread's cold words (threads with one x 4)
+  uint32_t cold_off;  // byte offset of this thread's first cold word
+  HEIC_HD int& cold(int j) const { return *reinterpret_cast<int*>(heic_cabac_smem + cold_off + (uint32_t)j * kColdStride); }
+  HEIC_HD const Arenas* arenas() const { return reinterpret_cast<const Arenas*>(heic_cabac_smem + kSmemArenasOff); }
+  HEIC_HD const TileParams* TP() const { return arenas()->tiles + (uint32_t)cold(CW_TILE); }
+  HEIC_HD const PicParams* PP() const { return arenas()->pics + TP()->pic; }
+  HEIC_HD uint32_t* tu_map_p() const { return arenas()->tu_map + TP()->tu_off; }
+  HEIC_HD int16_t* coeff_p(int c) const { return arenas()->coeff + TP()->coeff_off[c]; }
+  HEIC_HD uint8_t* ipm_p() const { return arenas()->ipm + TP()->map4_off; }
+  HEIC_HD uint8_t* ct_depth_p() const { return arenas()->ct_depth + TP()->map8_off; }
+  HEIC_HD uint8_t* qp_map_p() const { return arenas()->qp_map + TP()->map8_off; }
+  HEIC_HD uint32_t* sao_p() const { return arenas()->sao + TP()->sao_off; }
+#else
   const CabacTabs* T;
   uint8_t* ctx;
   const PicParams* pp;
@@ -384,13 +412,26 @@ struct Parser {
   int16_t *coeff0, *coeff1, *coeff2;
   uint8_t *ipm, *ct_depth, *qp_map;
   uint32_t* sao;
+  int cold_words[CW_COUNT];
+  HEIC_HD int& cold(int j) { return cold_words[j]; }
+  HEIC_HD const TileParams* TP() const { return tp; }
+  HEIC_HD const PicParams* PP() const { return pp; }
+  HEIC_HD uint32_t* tu_map_p() const { return tu_map; }
+  HEIC_HD int16_t* coeff_p(int c) const { return c == 0 ? coeff0 : (c == 1 ? coeff1 : coeff2); }
+  HEIC_HD uint8_t* ipm_p() const { return ipm; }
+  HEIC_HD uint8_t* ct_depth_p() const { return ct_depth; }
+  HEIC_HD uint8_t* qp_map_p() const { return qp_map; }
+  HEIC_HD uint32_t* sao_p() const { return sao; }
+#endif
   // QP state (8.6.1)
-  int is_cu_qp_delta_coded, cu_qp_delta_val, qp_y, last_qp_y, qp_y_pred, first_qg_in_row, qg_x, qg_y;
-  // current CU
-  int part_nxn, chroma_mode, cu_x, cu_y, cu_log2;
-  uint32_t pu_modes;  // IntraPredModeY of the (up to) four prediction blocks, 8 bits each (no indexed arrays: they
-                      // would live in local memory)
-  int err;
+  HEIC_HD int& is_cu_qp_delta_coded() { return cold(CW_QP_CODED); }
+  HEIC_HD int& cu_qp_delta_val() { return cold(CW_QP_DELTA); }
+  HEIC_HD int& qp_y() { return cold(CW_QP_Y); }
+  HEIC_HD int& last_qp_y() { return cold(CW_QP_LAST); }
+  HEIC_HD int& qp_y_pred() { return cold(CW_QP_PRED); }
+  HEIC_HD int& first_qg_in_row() { return cold(CW_QP_FIRST); }
+  HEIC_HD int& qg_x() { return cold(CW_QG_X); }
+  HEIC_HD int& qg_y() { return cold(CW_QG_Y); }
 
 #if defined(__CUDA_ARCH__)
   uint32_t ctx_off;  // byte offset of this thread's context table in the kernel's dynamic shared memory
@@ -488,6 +529,9 @@ struct Parser {
 
   // ---- 7.3.8.3 sao() (todo!() at slice.rs:249-251) -------------------------------------------
   HEIC_HD void parse_sao(int rx, int ry) {
+    const PicParams* pp = PP();
+    const TileParams* tp = TP();
+    uint32_t* sao = sao_p();
     uint32_t* p = sao + (size_t)(ry * pp->wctb + rx) * 4;
     int merge_left = 0, merge_up = 0;
     if (rx > 0) merge_left = dec(CTX_SAO_MERGE);
@@ -594,13 +638,14 @@ struct Parser {
   // Split into a prologue (transform_skip_flag, last significant position) and one call per 4x4 sub-block, so that the
   // same code serves the nested walk (host) and the flat per-sub-block loop of the device (coding_tree_unit).
   struct Rc {
-    int log2, c_idx, scan_idx, n, lg_sb, sb_w, sig_base, sig_off, last_sub_block, last_scan_pos;
-    int greater1_ctx, first_sub_block, tskip;
+    int log2, c_idx, scan_idx, sig_off, last_sub_block, last_scan_pos;
+    int greater1_ctx, first_sub_block, tskip, sign_hiding;
     int i;          // next sub-block (scan order, counting down)
     uint64_t csbf;  // coded_sub_block_flag, bit ys*8+xs
     int16_t* out;
   };
   HEIC_HD void rc_begin(Rc& r, int log2, int c_idx, int pred_mode, int16_t* out) {
+    const PicParams* pp = PP();
     const int n = 1 << log2;
     int tskip = 0;
     if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
@@ -641,23 +686,20 @@ HEIC_NO_UNROLL
     r.log2 = log2;
     r.c_idx = c_idx;
     r.scan_idx = scan_idx;
-    r.n = n;
-    r.lg_sb = lg_sb;
-    r.sb_w = sb_w;
-    r.sig_base = sig_base;
     r.sig_off = sig_off;
     r.last_sub_block = last_sub_block;
     r.last_scan_pos = last_scan_pos;
     r.greater1_ctx = 1;
     r.first_sub_block = 1;
     r.tskip = tskip;
+    r.sign_hiding = pp->sign_hiding;
     r.i = last_sub_block;
     r.csbf = 0;
     r.out = out;
   }
   HEIC_HD void rc_subblock(Rc& r) {  // sub-block r.i
-    const int log2 = r.log2, c_idx = r.c_idx, scan_idx = r.scan_idx, n = r.n, lg_sb = r.lg_sb, sb_w = r.sb_w;
-    const int sig_base = r.sig_base, sig_off = r.sig_off, last_sub_block = r.last_sub_block, last_scan_pos = r.last_scan_pos;
+    const int log2 = r.log2, c_idx = r.c_idx, scan_idx = r.scan_idx, n = 1 << log2, lg_sb = log2 - 2, sb_w = 1 << lg_sb;
+    const int sig_base = CTX_SIG + (c_idx ? 27 : 0), sig_off = r.sig_off, last_sub_block = r.last_sub_block, last_scan_pos = r.last_scan_pos;
     const int i = r.i;
     int16_t* out = r.out;
     uint64_t& csbf = r.csbf;
@@ -734,7 +776,7 @@ HEIC_NO_UNROLL
       beyond8 = m;
     }
 #endif
-    const int sign_hidden = pp->sign_hiding && (last_sig - first_sig > 3);
+    const int sign_hidden = r.sign_hiding && (last_sig - first_sig > 3);
     int g2 = 0;
     if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
     // coeff_sign_flag: one bypass bin per coefficient in scan order (none for the hidden one, which comes last):
@@ -783,67 +825,70 @@ HEIC_NO_UNROLL
 
   // ---- 8.6.1 ------------------------------------------------------------------------------------
   HEIC_HD void set_qp_pred(int x_qg, int y_qg) {
-    int qp_prev = first_qg_in_row ? tp->slice_qp : last_qp_y;
-    first_qg_in_row = 0;
+    const PicParams* pp = PP();
+    const TileParams* tp = TP();
+    const uint8_t* qp_map = qp_map_p();
+    int qp_prev = first_qg_in_row() ? tp->slice_qp : last_qp_y();
+    first_qg_in_row() = 0;
     int ctb_mask = (1 << pp->log2_ctb) - 1;
     int qa = qp_prev, qb = qp_prev;
     if (x_qg & ctb_mask) qa = qp_map[(y_qg >> 3) * pp->w8 + ((x_qg - 1) >> 3)];
     if (y_qg & ctb_mask) qb = qp_map[((y_qg - 1) >> 3) * pp->w8 + (x_qg >> 3)];
-    qp_y_pred = (qa + qb + 1) >> 1;
-    qp_y = qp_y_pred;
+    qp_y_pred() = (qa + qb + 1) >> 1;
+    qp_y() = qp_y_pred();
   }
 
   // ---- 7.3.8.10 transform_unit ------------------------------------------------------------------
   // z4: z-order index of the TU's 4x4 origin inside its CTB; ctb_addr: raster CTB address.  Split into the part before
   // the residuals (tu_begin), the choice of a component's residual block (tu_component) and the tu_map record (tu_end).
   struct Tu {
-    int log2, log2c, luma_mode, has_chroma, cbf_luma, cbf_cb, cbf_cr;
+    int log2, luma_mode, has_chroma, cbf_luma, cbf_cb, cbf_cr;
     uint32_t ti, ts;  // tu_map index; transform_skip_flag of the three components
-    size_t off_c;     // chroma coefficient offset
   };
   HEIC_HD void tu_begin(Tu& t, int x0, int y0, int log2, int blk_idx, int cbf_luma, int cbf_cb, int cbf_cr, uint32_t ctb_addr,
                         uint32_t z4) {
+    const PicParams* pp = PP();
     const int pb_shift = part_nxn ? cu_log2 - 1 : cu_log2;
     const int pu_idx = (((x0 - cu_x) >> pb_shift) & 1) | ((((y0 - cu_y) >> pb_shift) & 1) << 1);
     t.luma_mode = (int)((pu_modes >> (8 * pu_idx)) & 0xffu);
     t.has_chroma = pp->chroma && (log2 > 2 || blk_idx == 3);
     t.log2 = log2;
-    t.log2c = log2 > 2 ? log2 - 1 : 2;
     const int any_cbf = cbf_luma | cbf_cb | cbf_cr;  // 7.3.8.10: parent-inherited chroma cbfs count for blkIdx 0..2 too
     if (!t.has_chroma) cbf_cb = cbf_cr = 0;
     t.cbf_luma = cbf_luma;
     t.cbf_cb = cbf_cb;
     t.cbf_cr = cbf_cr;
-    if (any_cbf && pp->cu_qp_delta_enabled && !is_cu_qp_delta_coded) {
+    if (any_cbf && pp->cu_qp_delta_enabled && !is_cu_qp_delta_coded()) {
       // cu_qp_delta_abs: prefix TR cMax 5 (bin 0 ctx 0, bins 1-4 ctx 1) + EG0 suffix (decoder.rs:263-284)
       int v = 0;
       while (v < 5 && dec(CTX_CU_QP_DELTA + (v ? 1 : 0))) v++;
       if (v == 5) v += (int)egk_bypass(0);
       int neg = v ? byp() : 0;
-      is_cu_qp_delta_coded = 1;
-      cu_qp_delta_val = neg ? -v : v;
-      if (cu_qp_delta_val < -26 || cu_qp_delta_val > 25) fail(-3);
-      qp_y = (qp_y_pred + cu_qp_delta_val + 52) % 52;
+      is_cu_qp_delta_coded() = 1;
+      cu_qp_delta_val() = neg ? -v : v;
+      if (cu_qp_delta_val() < -26 || cu_qp_delta_val() > 25) fail(-3);
+      qp_y() = (qp_y_pred() + cu_qp_delta_val() + 52) % 52;
     }
     const int ctb4 = 1 << (pp->log2_ctb - 2);
     t.ti = ctb_addr * (uint32_t)(ctb4 * ctb4) + z4;
-    t.off_c = ((size_t)ctb_addr * (uint32_t)((ctb4 * ctb4) >> 2) + (z4 >> 2)) * 16;
     t.ts = 0;
   }
   // residual block of component c: false when its cbf is 0, else the arguments of rc_begin
   HEIC_HD bool tu_component(const Tu& t, int c, int& log2, int& pred_mode, int16_t*& dst) const {
     const int cbf = c == 0 ? t.cbf_luma : (c == 1 ? t.cbf_cb : t.cbf_cr);
     if (!cbf) return false;
-    dst = c == 0 ? coeff0 + (size_t)t.ti * 16 : (c == 1 ? coeff1 : coeff2) + t.off_c;
-    log2 = c ? t.log2c : t.log2;
+    // luma: 16 coefficients per tu_map entry; chroma: 4, at the entry of the 8x8 luma area the block belongs to (the CTB's
+    // entry count is a multiple of 4, so ti >> 2 is the chroma block index)
+    dst = c == 0 ? coeff_p(0) + (size_t)t.ti * 16 : coeff_p(c) + (size_t)(t.ti >> 2) * 16;
+    log2 = c ? (t.log2 > 2 ? t.log2 - 1 : 2) : t.log2;
     pred_mode = c ? chroma_mode : t.luma_mode;
     return true;
   }
   HEIC_HD void tu_end(const Tu& t) {
     const int ts0 = (int)(t.ts & 1u), ts1 = (int)((t.ts >> 1) & 1u), ts2 = (int)((t.ts >> 2) & 1u);
-    tu_map[t.ti] = 1u | ((uint32_t)(t.log2 - 2) << 1) | ((uint32_t)t.cbf_luma << 3) | ((uint32_t)t.cbf_cb << 4) |
+    tu_map_p()[t.ti] = 1u | ((uint32_t)(t.log2 - 2) << 1) | ((uint32_t)t.cbf_luma << 3) | ((uint32_t)t.cbf_cb << 4) |
                    ((uint32_t)t.cbf_cr << 5) | ((uint32_t)t.has_chroma << 6) | ((uint32_t)t.luma_mode << 7) |
-                   ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y << 19) | ((uint32_t)ts0 << 25) |
+                   ((uint32_t)chroma_mode << 13) | ((uint32_t)qp_y() << 19) | ((uint32_t)ts0 << 25) |
                    ((uint32_t)ts1 << 26) | ((uint32_t)ts2 << 27);
   }
   // ---- 7.3.8.8 transform_tree, walked iteratively in z-order over the CU's 4x4 blocks -----------
@@ -861,6 +906,7 @@ HEIC_NO_UNROLL
   // Descends from the largest block whose origin is t.z to its leaf (split_transform_flag, cbf_cb, cbf_cr, cbf_luma)
   // and starts that transform unit.
   HEIC_HD void tt_leaf(Tt& t, Tu& tu, uint32_t ctb_addr, uint32_t z4_cu) {
+    const PicParams* pp = PP();
     const int intra_split = part_nxn;
     const int max_depth = pp->max_trafo_depth_intra + intra_split;
     const uint32_t z = t.z;
@@ -927,6 +973,8 @@ HEIC_NO_UNROLL
 
   // ---- 8.4.2 ------------------------------------------------------------------------------------
   HEIC_HD int derive_luma_mode(int x, int y, int prev_flag, int mpm_idx, int rem) {
+    const PicParams* pp = PP();
+    const uint8_t* ipm = ipm_p();
     int cand_a = 1, cand_b = 1;
     if (x > 0) cand_a = ipm[(y >> 2) * pp->w4 + ((x - 1) >> 2)];
     if (y > 0 && ((y - 1) >> pp->log2_ctb) == (y >> pp->log2_ctb)) cand_b = ipm[((y - 1) >> 2) * pp->w4 + (x >> 2)];
@@ -963,6 +1011,8 @@ HEIC_NO_UNROLL
   // ---- 7.3.8.5 coding_unit (I slice) -------------------------------------------------------------
   // prediction part of the CU (everything before its transform tree)
   HEIC_HD void cu_begin(int x0, int y0, int log2) {
+    const PicParams* pp = PP();
+    uint8_t* ipm = ipm_p();
     const int n = 1 << log2;
     cu_x = x0;
     cu_y = y0;
@@ -971,12 +1021,12 @@ HEIC_NO_UNROLL
     if (pp->cu_qp_delta_enabled) {
       int mask = (1 << pp->log2_min_cu_qp_delta_size) - 1;
       int x_qg = x0 & ~mask, y_qg = y0 & ~mask;
-      if (x_qg != qg_x || y_qg != qg_y) {
-        qg_x = x_qg;
-        qg_y = y_qg;
+      if (x_qg != qg_x() || y_qg != qg_y()) {
+        qg_x() = x_qg;
+        qg_y() = y_qg;
         set_qp_pred(x_qg, y_qg);
       }
-      qp_y = (qp_y_pred + cu_qp_delta_val + 52) % 52;
+      qp_y() = (qp_y_pred() + cu_qp_delta_val() + 52) % 52;
     }
     if (log2 == pp->log2_min_cb) part_nxn = !dec(CTX_PART_MODE);  // decoder.rs:136-149
     if (part_nxn && log2 == 3 && pp->log2_min_tb >= 3) {
@@ -1015,11 +1065,13 @@ HEIC_NO_UNROLL
     }
   }
   HEIC_HD void cu_end() {
+    const PicParams* pp = PP();
+    uint8_t* qp_map = qp_map_p();
     // QpY of the CU (8.6.1): CuQpDeltaVal decoded anywhere inside the CU applies to all of it
     const int n = 1 << cu_log2;
     for (int yy = cu_y >> 3; yy < (cu_y + n) >> 3; yy++)
-      for (int xx = cu_x >> 3; xx < (cu_x + n) >> 3; xx++) qp_map[yy * pp->w8 + xx] = (uint8_t)qp_y;
-    last_qp_y = qp_y;
+      for (int xx = cu_x >> 3; xx < (cu_x + n) >> 3; xx++) qp_map[yy * pp->w8 + xx] = (uint8_t)qp_y();
+    last_qp_y() = qp_y();
   }
   HEIC_HD void coding_unit(int x0, int y0, int log2, uint32_t ctb_addr, uint32_t z4_cu) {
     cu_begin(x0, y0, log2);
@@ -1032,6 +1084,8 @@ HEIC_NO_UNROLL
   // One step of the walk: from the minimum-size block z (z-order inside the CTB) descend through split_cu_flag to the
   // coding unit that starts there.  False: the quadrant lies outside the picture and was skipped (z advanced).
   HEIC_HD bool ctu_next_cu(uint32_t& z, int x_ctb, int y_ctb, int& x0_out, int& y0_out, int& log2_out) {
+    const PicParams* pp = PP();
+    uint8_t* ct_depth = ct_depth_p();
     const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
     const int max_lvl = log2_ctb - log2_min_cb;
     int lvl = max_lvl;
@@ -1057,8 +1111,8 @@ HEIC_NO_UNROLL
         split = log2 > log2_min_cb;
       }
       if (pp->cu_qp_delta_enabled && log2 >= pp->log2_min_cu_qp_delta_size) {
-        is_cu_qp_delta_coded = 0;
-        cu_qp_delta_val = 0;
+        is_cu_qp_delta_coded() = 0;
+        cu_qp_delta_val() = 0;
       }
       if (!split) break;
       log2--;
@@ -1075,10 +1129,12 @@ HEIC_NO_UNROLL
   }
 
   HEIC_HD void coding_tree_unit(int rx, int ry) {
+    const PicParams* pp = PP();
+    const TileParams* tp = TP();
     const int log2_ctb = pp->log2_ctb, log2_min_cb = pp->log2_min_cb;
     const uint32_t ctb_addr = (uint32_t)(ry * pp->wctb + rx);
     const int x_ctb = rx << log2_ctb, y_ctb = ry << log2_ctb;
-    if (!pp->cu_qp_delta_enabled) qp_y = tp->slice_qp;
+    if (!pp->cu_qp_delta_enabled) qp_y() = tp->slice_qp;
     if (tp->sao_luma || tp->sao_chroma) parse_sao(rx, ry);
     const uint32_t n_min = 1u << (2 * (log2_ctb - log2_min_cb));
     uint32_t z = 0;
@@ -1106,17 +1162,17 @@ HEIC_NO_UNROLL
 // ------------------------------------------------------------------------------------------------
 template <int STRIDE, class Eng, class Sync>
 HEIC_HD uint32_t parse_rows(Parser<STRIDE, Eng>& P, const uint32_t* substreams, int slot, int n_slots, Sync& sync) {
-  const PicParams* pp = P.pp;
-  const TileParams* tp = P.tp;
+  const PicParams* pp = P.PP();
+  const TileParams* tp = P.TP();
   const int wpp = pp->wpp, wctb = pp->wctb, hctb = pp->hctb;
   const int n_ctb = wctb * hctb;
   uint32_t ctus = 0;
-  P.qp_y = P.last_qp_y = tp->slice_qp;
-  P.qp_y_pred = tp->slice_qp;
-  P.qg_x = P.qg_y = -1;
-  P.is_cu_qp_delta_coded = 0;
-  P.cu_qp_delta_val = 0;
-  P.first_qg_in_row = 1;
+  P.qp_y() = P.last_qp_y() = tp->slice_qp;
+  P.qp_y_pred() = tp->slice_qp;
+  P.qg_x() = P.qg_y() = -1;
+  P.is_cu_qp_delta_coded() = 0;
+  P.cu_qp_delta_val() = 0;
+  P.first_qg_in_row() = 1;
   P.e.bins = 0;
   // Every thread walks all of its (row, CTU) steps even after a failure, so that the wavefront
   // hand-shakes stay matched and no dependent row can hang; a failed thread just stops parsing.
@@ -1138,7 +1194,7 @@ HEIC_HD uint32_t parse_rows(Parser<STRIDE, Eng>& P, const uint32_t* substreams, 
             const uint8_t* src = sync.save_area(ry - 1);
             for (int i = 0; i < NUM_CTX; i++) P.st_ctx(i, src[i * Sync::kSaveStride]);
           }
-          P.first_qg_in_row = 1;
+          P.first_qg_in_row() = 1;
         }
         if (!P.err) P.coding_tree_unit(rx, ry);
         if (!P.err) {

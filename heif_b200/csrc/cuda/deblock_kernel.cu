@@ -43,34 +43,18 @@ struct Pic {
 
 // Is the edge through luma sample (x, y) at coordinate `pos` (x for a vertical edge, y for a horizontal one; a multiple
 // of 8) a transform-block edge?  Transform units of 4x4 and 8x8 always end on the 8-sample grid, and nothing is larger than
-// 32x32, so the edge is NOT one only if a 16x16 or 32x32 unit covers the sample and `pos` is not a multiple of its size: at
-// most two probes of tu_map (the 16- and the 32-aligned candidate origins), none on the 32-sample grid (CTB borders included).
+// 32x32, so the edge is NOT one only if a 16x16 or 32x32 unit covers the sample and `pos` is not a multiple of its size: two
+// probes of tu_map (the 16- and the 32-aligned candidate origins) instead of four.  Both are always issued -- independent
+// loads, no branch on the position: skipping them where `pos` makes them moot measured slower (14.5 vs 14.0 ms).
 __device__ __forceinline__ bool is_tu_edge(const Pic& p, int x, int y, int pos) {
-#if defined(HEIC_DEBLOCK_PROBE_UNCONDITIONAL)
-  // A/B variant: both probes always issued (independent loads, no branch on the position)
-  {
-    const int ctb4 = 1 << (p.log2_ctb - 2);
-    const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
-    const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
-    const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
-    const uint32_t w3 = tu[z & ~63u], w2 = tu[z & ~15u];
-    const bool in32 = (w3 & 7u) == (TU_ORIGIN | (3u << 1)) && (pos & 31) != 0;
-    const bool in16 = (w2 & 7u) == (TU_ORIGIN | (2u << 1)) && (pos & 15) != 0;
-    return !(in32 || in16);
-  }
-#endif
-  if ((pos & 31) == 0) return true;
   const int ctb4 = 1 << (p.log2_ctb - 2);
   const int rx = x >> p.log2_ctb, ry = y >> p.log2_ctb;
   const uint32_t z = interleave4((uint32_t)(x >> 2) & (ctb4 - 1)) | (interleave4((uint32_t)(y >> 2) & (ctb4 - 1)) << 1);
   const uint32_t* tu = p.tu_map + (size_t)(ry * p.wctb + rx) * (ctb4 * ctb4);
-  const uint32_t w3 = tu[z & ~63u];
-  bool inside = (w3 & 7u) == (TU_ORIGIN | (3u << 1));
-  if (pos & 15) {
-    const uint32_t w2 = tu[z & ~15u];
-    inside = inside || (w2 & 7u) == (TU_ORIGIN | (2u << 1));
-  }
-  return !inside;
+  const uint32_t w3 = tu[z & ~63u], w2 = tu[z & ~15u];
+  const bool in32 = (w3 & 7u) == (TU_ORIGIN | (3u << 1)) && (pos & 31) != 0;
+  const bool in16 = (w2 & 7u) == (TU_ORIGIN | (2u << 1)) && (pos & 15) != 0;
+  return !(in32 || in16);
 }
 __device__ __forceinline__ int qp_at(const Pic& p, int x, int y) { return p.qp_map[(y >> 3) * p.w8 + (x >> 3)]; }
 
