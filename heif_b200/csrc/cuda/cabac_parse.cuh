@@ -638,11 +638,15 @@ struct Parser {
   // Split into a prologue (transform_skip_flag, last significant position) and one call per 4x4 sub-block, so that the
   // same code serves the nested walk (host) and the flat per-sub-block loop of the device (coding_tree_unit).
   struct Rc {
-    int log2, c_idx, scan_idx, sig_off, last_sub_block, last_scan_pos;
-    int greater1_ctx, first_sub_block, tskip, sign_hiding;
+    // the block's constants and the greater1 state carried between sub-blocks, packed (the structure is live across every
+    // decoding call of the block, and the kernel is bound by its registers):
+    //   log2 | c_idx << 3 | scan_idx << 5 | sig_off << 7 | last_sub_block << 13 | last_scan_pos << 19 | tskip << 23 |
+    //   sign_hiding << 24 | greater1_ctx << 25 | first_sub_block << 27
+    uint32_t k;
     int i;          // next sub-block (scan order, counting down)
     uint64_t csbf;  // coded_sub_block_flag, bit ys*8+xs
     int16_t* out;
+    HEIC_HD int tskip() const { return (int)((k >> 23) & 1u); }
   };
   HEIC_HD void rc_begin(Rc& r, int log2, int c_idx, int pred_mode, int16_t* out) {
     const PicParams* pp = PP();
@@ -683,28 +687,23 @@ HEIC_NO_UNROLL
     const int sig_base = CTX_SIG + (c_idx ? 27 : 0);
     // sigCtx offset for the non-4x4, non-DC case (9.3.4.2.5)
     const int sig_off = c_idx == 0 ? ((log2 == 3) ? (scan_idx == 0 ? 9 : 15) : 21) : ((log2 == 3) ? 9 : 12);
-    r.log2 = log2;
-    r.c_idx = c_idx;
-    r.scan_idx = scan_idx;
-    r.sig_off = sig_off;
-    r.last_sub_block = last_sub_block;
-    r.last_scan_pos = last_scan_pos;
-    r.greater1_ctx = 1;
-    r.first_sub_block = 1;
-    r.tskip = tskip;
-    r.sign_hiding = pp->sign_hiding;
+    r.k = (uint32_t)log2 | ((uint32_t)c_idx << 3) | ((uint32_t)scan_idx << 5) | ((uint32_t)sig_off << 7) |
+          ((uint32_t)last_sub_block << 13) | ((uint32_t)last_scan_pos << 19) | ((uint32_t)tskip << 23) |
+          ((uint32_t)(pp->sign_hiding ? 1 : 0) << 24) | (1u << 25) | (1u << 27);
     r.i = last_sub_block;
     r.csbf = 0;
     r.out = out;
   }
   HEIC_HD void rc_subblock(Rc& r) {  // sub-block r.i
-    const int log2 = r.log2, c_idx = r.c_idx, scan_idx = r.scan_idx, n = 1 << log2, lg_sb = log2 - 2, sb_w = 1 << lg_sb;
-    const int sig_base = CTX_SIG + (c_idx ? 27 : 0), sig_off = r.sig_off, last_sub_block = r.last_sub_block, last_scan_pos = r.last_scan_pos;
+    const int log2 = (int)(r.k & 7u), c_idx = (int)((r.k >> 3) & 3u), scan_idx = (int)((r.k >> 5) & 3u), n = 1 << log2, lg_sb = log2 - 2,
+              sb_w = 1 << lg_sb;
+    const int sig_base = CTX_SIG + (c_idx ? 27 : 0), sig_off = (int)((r.k >> 7) & 63u), last_sub_block = (int)((r.k >> 13) & 63u),
+              last_scan_pos = (int)((r.k >> 19) & 15u);
     const int i = r.i;
     int16_t* out = r.out;
     uint64_t& csbf = r.csbf;
-    int& greater1_ctx = r.greater1_ctx;
-    int& first_sub_block = r.first_sub_block;
+    int greater1_ctx = (int)((r.k >> 25) & 3u);
+    int first_sub_block = (int)((r.k >> 27) & 1u);
     uint32_t sxy = scan_xy(scan_idx, lg_sb, i);
     const int xs = (int)(sxy & 15u), ys = (int)(sxy >> 4);
     int right = (xs < sb_w - 1) ? (int)((csbf >> (ys * 8 + xs + 1)) & 1u) : 0;
@@ -776,7 +775,8 @@ HEIC_NO_UNROLL
       beyond8 = m;
     }
 #endif
-    const int sign_hidden = r.sign_hiding && (last_sig - first_sig > 3);
+    r.k = (r.k & ~(7u << 25)) | ((uint32_t)greater1_ctx << 25);  // first_sub_block = 0, greater1Ctx for the next sub-block
+    const int sign_hidden = ((r.k >> 24) & 1u) && (last_sig - first_sig > 3);
     int g2 = 0;
     if (last_g1_pos >= 0) g2 = dec(CTX_GT2 + (c_idx ? 4 : 0) + ctx_set);
     // coeff_sign_flag: one bypass bin per coefficient in scan order (none for the hidden one, which comes last):
@@ -820,7 +820,7 @@ HEIC_NO_UNROLL
     Rc r;
     rc_begin(r, log2, c_idx, pred_mode, out);
     for (; r.i >= 0 && !err; r.i--) rc_subblock(r);
-    return r.tskip;
+    return r.tskip();
   }
 
   // ---- 8.6.1 ------------------------------------------------------------------------------------
