@@ -82,7 +82,7 @@ extern __shared__ __align__(16) unsigned char heic_cabac_smem[];
 struct Engine {
   const uint8_t* data;   // 2-byte aligned on the device
   uint32_t pos, end;     // next halfword to fetch (even byte offset from data), substream end
-  uint32_t look0, look1; // prefetched halfwords (big-endian values)
+  uint32_t look0, look1; // prefetched halfwords (look0: big-endian value; look1: see load16_raw)
   uint32_t range, val;
   int nbits;
   uint32_t bins;
@@ -97,6 +97,25 @@ struct Engine {
     uint32_t h = ((uint32_t)data[p] << 8) | (p + 1 < end ? data[p + 1] : 0u);
 #endif
     if (p + 1u >= end) h &= 0xff00u;
+    return h;
+  }
+  // The device keeps the second prefetched halfword as it came from memory and turns it into the big-endian value only
+  // when it moves up to `look0`, one refill later: the byte swap right behind the load made every refill wait for the
+  // load's latency (4 % of the kernel's stall samples).
+  HEIC_HD uint32_t load16_raw(uint32_t p) const {  // p even
+#if defined(__CUDA_ARCH__)
+    return p < end ? (uint32_t)*reinterpret_cast<const uint16_t*>(data + p) : 0u;
+#else
+    return load16(p);
+#endif
+  }
+  HEIC_HD uint32_t finish16(uint32_t h, uint32_t p) const {
+#if defined(__CUDA_ARCH__)
+    h = __byte_perm(h, 0u, 0x4401);
+    if (p + 1u >= end) h &= 0xff00u;
+#else
+    (void)p;
+#endif
     return h;
   }
   // 9.3.2.5 (arithmetic.rs:23-38): ivlCurrRange = 510, ivlOffset = read_bits(9)
@@ -114,7 +133,7 @@ struct Engine {
       pos = start + 2;
     }
     look0 = load16(pos);
-    look1 = load16(pos + 2);
+    look1 = load16_raw(pos + 2);
     pos += 4;
   }
   HEIC_HD bool offset_is_illegal() const { return (val >> 22) >= 510u; }
@@ -124,8 +143,8 @@ struct Engine {
     if (nbits < 7) {
       val |= look0 << (6 - nbits);
       nbits += 16;
-      look0 = look1;
-      look1 = load16(pos);
+      look0 = finish16(look1, pos - 2u);
+      look1 = load16_raw(pos);
       pos += 2;
     }
   }
