@@ -15,6 +15,7 @@
 // through HBM/L2 so that shared memory only holds the live context tables.
 #include <cuda_runtime.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "cabac_parse.cuh"
@@ -186,7 +187,19 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   sync.use1 = use + 1;
   if (!active) *sync.aborted() = use + 1;
 
+#if HEIC_CABAC_TRACE  // group timeline for tools/cabac_trace.py: one line per (CTA, group, warp)
+  unsigned long long t_begin;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
+#endif
   const uint32_t ctus = parse_rows<TILES>(P, A.substreams + tp->sub_first, slot, n_slots, sync);
+#if HEIC_CABAC_TRACE
+  {
+    unsigned long long t_end;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+    const unsigned bins_w = __reduce_add_sync(0xffffffffu, active ? P.e.bins : 0u);
+    if (lane == 0) printf("CT %u %u %d %d %llu %llu %u %u\n", blockIdx.x, group, use, slot, t_begin, t_end, bins_w, tp->bs_len);
+  }
+#endif
   if (active) {
     atomicAdd(&A.status[tile].bins, P.e.bins);
     atomicAdd(&A.status[tile].ctus, ctus);

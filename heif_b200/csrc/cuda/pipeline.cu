@@ -114,6 +114,8 @@ struct heic_b200_ctx {
                                  // critical-path lane, not the sum of its lanes, so full warps are the cheapest)
   int intra_slots = 0;           // 0: automatic (wavefront for small batches, one warp per picture for large)
   int intra_single_warp_tiles = 2048;
+  int cabac_group_cap_pct = 0;   // > 0: a group's slice bytes are capped at this per cent of (batch slice bytes / resident CTAs), so the
+                                 // heaviest groups -- the kernel's critical path -- carry fewer than 32 lanes
   int cabac_plain_sort = 0;      // measurement knob: plain size sort, copies of a slice may share a warp (bench.py's upper bound)
   int cabac_resident = 0;        // persistent CABAC CTAs to launch; 0: as many as are resident at once (tests use 2)
   int cabac_persistent = 1;      // large batches: CABAC CTAs take group after group, warp by warp (no ramp-up / drain per group)
@@ -325,6 +327,7 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
   }
   rgb_pitch = max_rgb_pitch;
   rgb_image_stride = up(max_rgb_bytes, 256);
+  if (tiles.size() >= (1u << 24)) bail(HEIC_E_UNSUPPORTED, "more than 2^24 tiles in one batch (the transform lists keep the tile index in 24 bits)");
 
   // ---- CABAC launch classes: tiles with the same wavefront shape, heaviest first, TILES per CTA ----------
   // few tiles: a warp per substream finishes a 12 MP image in about half the time of the 32-tiles-per-CTA mapping
@@ -393,11 +396,20 @@ void heic_b200_batch::load(const heic_image_desc* imgs, uint32_t n_imgs, bool wi
           runs.push_back({i, j - i});
           i = j;
         }
+        uint64_t cap = ~0ull;
+        if (ctx->cabac_group_cap_pct > 0) {
+          uint64_t total = 0;
+          for (uint32_t t : v) total += tiles[t].bs_len;
+          cap = total / (uint64_t)(ctx->n_sm * 3) * (uint64_t)ctx->cabac_group_cap_pct / 100u;
+        }
         size_t head = 0;  // runs before `head` are exhausted
         while (head < runs.size()) {
           int n = 0;
+          uint64_t wsum = 0;
           for (size_t r = head; r < runs.size() && n < tpc; r++) {
             if (!runs[r].left) continue;
+            if (n > 0 && wsum + tiles[v[runs[r].first]].bs_len > cap) break;  // sorted: the later runs are no lighter than allowed either
+            wsum += tiles[v[runs[r].first]].bs_len;
             order.push_back(v[runs[r].first++]);
             runs[r].left--;
             n++;
@@ -664,6 +676,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_persistent = env_int("HEIC_B200_CABAC_PERSISTENT", 1) != 0;
     c->cabac_resident = std::max(0, env_int("HEIC_B200_CABAC_RESIDENT", 0));
     c->cabac_plain_sort = env_int("HEIC_B200_CABAC_PLAIN_SORT", 0) != 0;
+    c->cabac_group_cap_pct = std::max(0, env_int("HEIC_B200_CABAC_GROUP_CAP", 0));
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(0, env_int("HEIC_B200_PIPE_SLOTS", 0)));
     *out_ctx = c.release();
     return 0;

@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_
   __syncthreads();
   const bool chroma = pp->chroma != 0;
   // kListIter coalesced 16-byte loads per thread (n_tu and tu_off are multiples of 16)
-  uint32_t cls[kListIter][4];
+  uint32_t cls[kListIter][4], w_all[kListIter][4];
   unsigned long long mine = 0;  // items of this thread per class, 12 bits each
 #pragma unroll
   for (int it = 0; it < kListIter; it++) {
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_
     const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
     for (int e = 0; e < 4; e++) {
+      w_all[it][e] = w[e];
       cls[it][e] = 0x1ffu;
       if (w[e]) {
         cls[it][e] = classify(w[e], chroma);
@@ -179,8 +181,11 @@ __global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_
       for (int c = 0; c < 3; c++) {
         const uint32_t k = (cls[it][e] >> (3 * c)) & 7u;
         if (k < LIST_CLASSES) {
+          // the block's QpY and transform_skip_flag ride in the item, so the transform kernels never touch tu_map again
+          // (for a 4x4 block that read was a 32-byte sector per 64 bytes of payload)
+          const uint32_t we = w_all[it][e];
           uint2_t v;
-          v.x = tile;
+          v.x = tile | (tu_qp(we) << 24) | (tu_tskip(we, c) << 30);
           v.y = (i0 + e) | ((uint32_t)c << 30);
           A.tu_list[(size_t)cta_base[k] + warp_base[warp][k] + ((uint32_t)(run >> (12 * k)) & 0xfffu)] = v;
           run += 1ull << (12 * k);
@@ -195,22 +200,23 @@ struct Item {
   const PicParams* pp;
   const TileParams* tp;
   int16_t* blk;
-  uint32_t w;
+  int qp, tskip;
   int cidx;
 };
 __device__ __forceinline__ Item fetch_item(const Arenas& A, uint2_t it) {
   Item r;
-  r.tp = A.tiles + it.x;
+  r.tp = A.tiles + (it.x & 0xffffffu);
   r.pp = A.pics + r.tp->pic;
   const uint32_t entry = it.y & 0x3fffffffu;
   r.cidx = (int)(it.y >> 30);
-  r.w = A.tu_map[r.tp->tu_off + entry];
+  r.qp = (int)((it.x >> 24) & 63u);
+  r.tskip = (int)((it.x >> 30) & 1u);
   // luma: 16 coefficients per tu_map entry; chroma: 4, at the entry of the 8x8 luma area the block belongs to
   r.blk = A.coeff + r.tp->coeff_off[r.cidx] + (r.cidx ? (size_t)(entry & ~3u) * 4 : (size_t)entry * 16);
   return r;
 }
 __device__ __forceinline__ int item_scale(const Item& t) {  // levelScale[qP % 6] << (qP / 6), 8.6.2 / 8.6.4.2
-  int qp = (int)tu_qp(t.w);
+  int qp = t.qp;
   if (t.cidx) {
     int qpi = qp + (t.cidx == 1 ? t.pp->pps_cb_qp_offset + t.tp->slice_cb_qp_offset : t.pp->pps_cr_qp_offset + t.tp->slice_cr_qp_offset);
     qpi = min(57, max(0, qpi));
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, 
     const Item item = fetch_item(A, it);  // item 0 of tile 0 for the idle lanes of the last step: read, never written
     int16_t* blk = item.blk;
     if (col == 0) blk_of[warp][k] = blk;
-    const bool tskip = active && tu_tskip(item.w, item.cidx);
+    const bool tskip = active && item.tskip;
     // ---- DC-only blocks (every block of this warp step has at most its DC coefficient; most large blocks of smooth
     // pictures): both 1-D passes of a lone DC term are a multiplication by 64, so every sample of the block is the same
     // value -- no butterflies, no transpose tile, just the fill.  Decided on the raw levels, warp-uniformly.
@@ -387,6 +393,329 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) transform_kernel(Arenas A, 
   }
 }
 
+// ---- n = 16, 32 on the tensor cores: the block as two integer matrix products ---------------------------------------
+// T = M^T X (columns, + 64 >> 7, clip) and R = T M (rows, + 2048 >> 12, clip) are dense contractions over 16 / 32 terms with
+// an 8-bit constant matrix.  A 16-bit operand is split as 256 * hi (signed byte) + lo (unsigned byte), so each product is two
+// `mma.sync.m16n8k{16,32}` with s8 x s8 and s8 x u8 operands and exact s32 accumulation (|sum| <= 32 * 90 * 32768 < 2^31): the
+// same integers as the butterflies, hence the same clipped results.
+//  * The contraction index may be permuted freely as long as both operands agree.  `ldmatrix.trans` hands a thread the
+//    coefficients X[8q + 2t][c], X[8q + 2t + 1][c] (q = 0..3) of its column c; their high / low bytes gathered with one
+//    PRMT each are the B fragment of the column pass for the order j = {2t, 2t+1, 8+2t, 9+2t | 16+2t, 17+2t, 24+2t, 25+2t}.
+//  * In that same order the accumulator fragments of the column pass (thread: T[r][8n + 2t], T[r][8n + 2t + 1]) ARE the A
+//    fragments of the row pass -- the two passes are joined in registers, no shared-memory transpose, no shuffles.
+//  * One set of eight constant registers per thread (M in the permuted order) serves as A of the first pass and B of the
+//    second.
+// One block per warp step; levels are loaded and scaled 16 bytes at a time, the residual leaves in 4-byte pieces that
+// complete whole sectors within the warp's store sequence.
+struct DctBytes {
+  int8_t m[32][32];
+};
+constexpr DctBytes make_dct_bytes() {
+  DctBytes t{};
+  for (int j = 0; j < 32; j++)
+    for (int i = 0; i < 32; i++) t.m[j][i] = (int8_t)dct32(j, i);
+  return t;
+}
+__device__ const DctBytes kDctBytes = make_dct_bytes();
+
+__device__ __forceinline__ void mma_k32(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1, int a_unsigned,
+                                        int b_unsigned) {
+  if (b_unsigned)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else if (a_unsigned)
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_k16(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, int a_unsigned, int b_unsigned) {
+  if (b_unsigned)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+  else if (a_unsigned)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+// high / low bytes of four 16-bit values held as two packed pairs
+__device__ __forceinline__ uint32_t hi_bytes(uint32_t p01, uint32_t p23) { return __byte_perm(p01, p23, 0x7531); }
+__device__ __forceinline__ uint32_t lo_bytes(uint32_t p01, uint32_t p23) { return __byte_perm(p01, p23, 0x6420); }
+
+// two s32 values saturated to s16 and packed (lo in the low half): clip16 x 2 + pack in one instruction
+__device__ __forceinline__ uint32_t sat_pack16(int lo, int hi) {
+  uint32_t d;
+  asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+  return d;
+}
+
+// 8.6.4.2 scaling of the eight levels of one 16-byte piece: m = the piece's scaling factors (8 bytes), ms = factor * levelScale.
+// WIDE: some level of the block may overflow the 32-bit product (decided once per block from the OR of the magnitudes).
+template <int BD_SHIFT, bool WIDE, bool TSKIP>
+__device__ __forceinline__ uint4 scale_piece(uint4 raw, uint2 mm, int scale) {
+  uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    int v2[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int lvl = hh ? (int)w[k] >> 16 : (int)(int16_t)(w[k] & 0xffffu);
+      const int mi = 2 * k + hh;
+      const int ms = (int)(((mi < 4 ? mm.x : mm.y) >> (8 * (mi & 3))) & 0xffu) * scale;
+      int v;
+      if (!WIDE) {
+        v = (lvl * ms + (1 << (BD_SHIFT - 1))) >> BD_SHIFT;
+      } else {
+        long long p = ((long long)lvl * ms + (1ll << (BD_SHIFT - 1))) >> BD_SHIFT;
+        v = (int)min(32767ll, max(-32768ll, p));
+      }
+      if (TSKIP) v = ((clip16(v) << 7) + 2048) >> 12;  // transform skip: the rotation of 8.6.4.2 on the scaled coefficient
+      v2[hh] = v;
+    }
+    w[k] = sat_pack16(v2[0], v2[1]);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// do all products |level| * factor of a block fit 31 bits?  `mag`: OR over the block of the levels' magnitudes-or-complements
+__device__ __forceinline__ bool products_fit(uint32_t mag, int max_ms) { return (32 - __clz(mag)) + (32 - __clz((uint32_t)max_ms)) <= 30; }
+// OR of |x|-ish bit patterns of the two 16-bit halves of w (x ^ (x >> 15) has the magnitude's leading bit)
+__device__ __forceinline__ uint32_t mag_bits(uint32_t w) {
+  const int lo = (int)(int16_t)(w & 0xffffu), hi = (int)w >> 16;
+  return (uint32_t)(lo ^ (lo >> 31)) | (uint32_t)(hi ^ (hi >> 31));
+}
+
+template <int N>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, N == 32 ? 4 : 8) transform_mma_kernel(Arenas A, int cls) {
+  constexpr int LOG2 = N == 16 ? 4 : 5;
+  constexpr int NT = N / 8;    // 8-column tiles
+  constexpr int MT = N / 16;   // 16-row tiles
+  constexpr int SB = 2 * N + 16;  // row stride of the staging tile in bytes: 8 consecutive rows fall into distinct banks
+  constexpr int VEC = N * N / 8 / 32;  // 16-byte pieces of a block per lane
+  __shared__ __align__(16) unsigned char tile_all[kWarpsPerCta][N * SB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t count = A.list_count[cls * LIST_COUNT_STRIDE];
+  const uint2_t* list = A.tu_list + A.list_off[cls];
+  unsigned char* tile = tile_all[warp];
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  // M in the permuted contraction order: cb[h][n] = bytes M[j][8n + g] for j = 16h + {2t, 2t+1, 8+2t, 9+2t}
+  uint32_t cb[N / 16][NT];
+#pragma unroll
+  for (int h = 0; h < N / 16; h++)
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int s4 = 0; s4 < 4; s4++) {
+        const int j = 16 * h + 2 * t + (s4 & 1) + 8 * (s4 >> 1);
+        v |= (uint32_t)(uint8_t)kDctBytes.m[j * (32 / N)][8 * n + g] << (8 * s4);
+      }
+      cb[h][n] = v;
+    }
+  for (uint32_t idx = blockIdx.x * kWarpsPerCta + warp; idx < count; idx += gridDim.x * kWarpsPerCta) {
+    const Item item = fetch_item(A, list[idx]);
+    uint4* blk = reinterpret_cast<uint4*>(item.blk);
+    uint4 raw[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; q++) raw[q] = blk[q * 32 + lane];
+    const bool tskip = item.tskip != 0;
+    uint32_t other = 0, mag = 0;
+#pragma unroll
+    for (int q = 0; q < VEC; q++) {
+      other |= (q == 0 && lane == 0 ? raw[q].x & 0xffff0000u : raw[q].x) | raw[q].y | raw[q].z | raw[q].w;
+      mag |= mag_bits(raw[q].x) | mag_bits(raw[q].y) | mag_bits(raw[q].z) | mag_bits(raw[q].w);
+    }
+    const int scale = item_scale(item);
+    const uint8_t* m = nullptr;
+    if (item.pp->scaling_enabled && !tskip) {
+      const ScalingSet* sc = A.scaling + item.pp->scaling_set;
+      m = N == 16 ? sc->f16[item.cidx] : sc->f32[item.cidx];
+    }
+    constexpr int BD_SHIFT = LOG2 + 3;  // BitDepth + log2(nTbS) - 5, 8-bit
+    if (!__any_sync(0xffffffffu, other != 0) && !tskip) {
+      // DC only: both passes of a lone DC term multiply by 64, every sample of the block gets the same value
+      const int lvl = (int)(int16_t)(__shfl_sync(0xffffffffu, raw[0].x, 0) & 0xffffu);
+      const long long p = ((long long)lvl * ((m ? (int)m[0] : 16) * scale) + (1ll << (BD_SHIFT - 1))) >> BD_SHIFT;
+      const int dc = (int)min(32767ll, max(-32768ll, p));
+      const int t1 = clip16((64 * dc + 64) >> 7);
+      const uint32_t vv = ((uint32_t)clip16((64 * t1 + 2048) >> 12) & 0xffffu) * 0x10001u;
+#pragma unroll
+      for (int q = 0; q < VEC; q++) blk[q * 32 + lane] = make_uint4(vv, vv, vv, vv);
+      continue;
+    }
+    // ---- scaling (8.6.4.2), in the layout of the load: lane owns 8 consecutive coefficients of a row per piece ----
+    const bool narrow = products_fit(__reduce_or_sync(0xffffffffu, mag), (m ? 255 : 16) * scale);
+    if (tskip) {  // warp-uniform (one block per warp step): no transform, the scaled coefficients rotated
+#pragma unroll
+      for (int q = 0; q < VEC; q++) blk[q * 32 + lane] = scale_piece<BD_SHIFT, true, true>(raw[q], make_uint2(0x10101010u, 0x10101010u), scale);
+      continue;
+    }
+#pragma unroll
+    for (int q = 0; q < VEC; q++) {
+      const int e0 = (q * 32 + lane) * 8;  // element index of the piece
+      uint2 mm = make_uint2(0x10101010u, 0x10101010u);
+      if (m) mm = *reinterpret_cast<const uint2*>(m + e0);
+      const uint4 sc4 = narrow ? scale_piece<BD_SHIFT, false, false>(raw[q], mm, scale) : scale_piece<BD_SHIFT, true, false>(raw[q], mm, scale);
+      *reinterpret_cast<uint4*>(tile + (e0 / N) * SB + (e0 % N) * 2) = sc4;
+    }
+    __syncwarp();
+    // ---- column pass: T = M^T X ----
+    int acc[MT][NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; n++) {
+      uint32_t r[4];
+      if (N == 32) {
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(tile_s + (uint32_t)(lane * SB + n * 16)));
+      } else {
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                     : "=r"(r[0]), "=r"(r[1])
+                     : "r"(tile_s + (uint32_t)((lane & 15) * SB + n * 16)));
+        r[2] = r[3] = 0;
+      }
+      const uint32_t h0 = hi_bytes(r[0], r[1]), l0 = lo_bytes(r[0], r[1]);
+      const uint32_t h1 = hi_bytes(r[2], r[3]), l1 = lo_bytes(r[2], r[3]);
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) acc[mt][n][k] = 0;
+        if (N == 32) {
+          mma_k32(acc[mt][n], cb[0][2 * mt], cb[0][2 * mt + 1], cb[1][2 * mt], cb[1][2 * mt + 1], h0, h1, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; k++) acc[mt][n][k] = acc[mt][n][k] * 256 + 64;  // the pass's rounding offset rides along
+          mma_k32(acc[mt][n], cb[0][2 * mt], cb[0][2 * mt + 1], cb[1][2 * mt], cb[1][2 * mt + 1], l0, l1, 0, 1);
+        } else {
+          mma_k16(acc[mt][n], cb[0][2 * mt], cb[0][2 * mt + 1], h0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; k++) acc[mt][n][k] = acc[mt][n][k] * 256 + 64;
+          mma_k16(acc[mt][n], cb[0][2 * mt], cb[0][2 * mt + 1], l0, 0, 1);
+        }
+      }
+    }
+    // ---- row pass: R = T M, A fragments straight from the accumulators ----
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+      uint32_t ah[4], al[4];  // a0: row g, first half of the contraction; a1: row g + 8; a2, a3: second half
+#pragma unroll
+      for (int hf = 0; hf < N / 16; hf++)
+#pragma unroll
+        for (int up = 0; up < 2; up++) {
+          const uint32_t p01 = sat_pack16(acc[mt][2 * hf][2 * up] >> 7, acc[mt][2 * hf][2 * up + 1] >> 7);
+          const uint32_t p23 = sat_pack16(acc[mt][2 * hf + 1][2 * up] >> 7, acc[mt][2 * hf + 1][2 * up + 1] >> 7);
+          ah[2 * hf + up] = hi_bytes(p01, p23);
+          al[2 * hf + up] = lo_bytes(p01, p23);
+        }
+#pragma unroll
+      for (int n = 0; n < NT; n++) {
+        int d[4] = {0, 0, 0, 0};
+        if (N == 32) {
+          mma_k32(d, ah[0], ah[1], ah[2], ah[3], cb[0][n], cb[1][n], 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; k++) d[k] = d[k] * 256 + 2048;
+          mma_k32(d, al[0], al[1], al[2], al[3], cb[0][n], cb[1][n], 1, 0);
+        } else {
+          mma_k16(d, ah[0], ah[1], cb[0][n], 0, 0);
+#pragma unroll
+          for (int k = 0; k < 4; k++) d[k] = d[k] * 256 + 2048;
+          mma_k16(d, al[0], al[1], cb[0][n], 1, 0);
+        }
+        uint32_t* out = reinterpret_cast<uint32_t*>(item.blk);
+        out[((16 * mt + g) * N + 8 * n + 2 * t) >> 1] = sat_pack16(d[0] >> 12, d[1] >> 12);
+        out[((16 * mt + g + 8) * N + 8 * n + 2 * t) >> 1] = sat_pack16(d[2] >> 12, d[3] >> 12);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// 8x8 blocks, four per warp step (a block is 128 contiguous bytes; a lane loads one 16-byte row of one block).  Two blocks
+// share an MMA: the contraction index is (block, j), A is
+// block-diagonal [M^T 0; 0 M^T] for the column pass, and in the row pass each block's T occupies its own eight rows of A with
+// the other half of the contraction zero.  One constant register per thread.
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 8) transform_mma8_kernel(Arenas A, int cls) {
+  __shared__ __align__(16) unsigned char tile_all[kWarpsPerCta][4 * 128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t count = A.list_count[cls * LIST_COUNT_STRIDE];
+  const uint2_t* list = A.tu_list + A.list_off[cls];
+  unsigned char* tile = tile_all[warp];
+  const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
+  // bytes M8[2t][g], M8[2t+1][g] (M8[j][i] = dct32(4j, i)) in the low / high half of the contraction quad
+  const uint32_t c2 = (uint32_t)(uint8_t)kDctBytes.m[4 * (2 * t)][g] | ((uint32_t)(uint8_t)kDctBytes.m[4 * (2 * t + 1)][g] << 8);
+  const uint32_t c_lo = c2, c_hi = c2 << 16;
+  const uint32_t steps = (count + 3) / 4;
+  const int kb = lane >> 3;  // block of the step this lane loads a row of
+  for (uint32_t step = blockIdx.x * kWarpsPerCta + warp; step < steps; step += gridDim.x * kWarpsPerCta) {
+    const uint32_t idx = step * 4 + kb;
+    const bool active = idx < count;
+    uint2_t it;
+    it.x = it.y = 0;
+    if (active) it = list[idx];
+    const Item item = fetch_item(A, it);  // item 0 of tile 0 for the idle lanes of the last step: read, never written
+    uint4* row = reinterpret_cast<uint4*>(item.blk) + (lane & 7);
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (active) raw = *row;
+    const int scale = item_scale(item);
+    const bool tskip = active && item.tskip;
+    uint2 mm = make_uint2(0x10101010u, 0x10101010u);
+    if (item.pp->scaling_enabled && !tskip) mm = *reinterpret_cast<const uint2*>((A.scaling + item.pp->scaling_set)->f8[item.cidx] + (lane & 7) * 8);
+    const uint32_t mag = mag_bits(raw.x) | mag_bits(raw.y) | mag_bits(raw.z) | mag_bits(raw.w);
+    const bool narrow = products_fit(__reduce_or_sync(0xffffffffu, mag), __reduce_max_sync(0xffffffffu, (item.pp->scaling_enabled ? 255 : 16) * scale));
+    const bool any_tskip = __any_sync(0xffffffffu, tskip);
+    uint4 sc4;
+    if (any_tskip) {  // rare: the skipped blocks are finished here, the others take the wide form
+      sc4 = tskip ? scale_piece<6, true, true>(raw, mm, scale) : scale_piece<6, true, false>(raw, mm, scale);
+      if (tskip) {
+        *row = sc4;
+        sc4 = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
+      sc4 = narrow ? scale_piece<6, false, false>(raw, mm, scale) : scale_piece<6, true, false>(raw, mm, scale);
+    }
+    *reinterpret_cast<uint4*>(tile + lane * 16) = sc4;
+    __syncwarp();
+    uint32_t r[4];  // block b: X_b[2t][g], X_b[2t+1][g]
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(tile_s + (uint32_t)(lane * 16)));
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {  // blocks 2 pr, 2 pr + 1
+      int acc[4] = {0, 0, 0, 0};
+      mma_k16(acc, c_lo, c_hi, hi_bytes(r[2 * pr], r[2 * pr + 1]), 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) acc[k] = acc[k] * 256 + 64;
+      mma_k16(acc, c_lo, c_hi, lo_bytes(r[2 * pr], r[2 * pr + 1]), 0, 1);
+      // T_b[g][2t], T_b[g][2t+1] (b = 2 pr: acc[0..1], b = 2 pr + 1: acc[2..3]) -> A of the row pass, second half zero
+      const uint32_t p0 = sat_pack16(acc[0] >> 7, acc[1] >> 7), p1 = sat_pack16(acc[2] >> 7, acc[3] >> 7);
+      int d[4] = {0, 0, 0, 0};
+      mma_k16(d, hi_bytes(p0, 0u), hi_bytes(p1, 0u), c_lo, 0, 0);
+#pragma unroll
+      for (int k = 0; k < 4; k++) d[k] = d[k] * 256 + 2048;
+      mma_k16(d, lo_bytes(p0, 0u), lo_bytes(p1, 0u), c_lo, 1, 0);
+      // R_b[g][2t], R_b[g][2t+1]: the lanes of a quad complete a 16-byte row, the warp a whole 128-byte block
+#pragma unroll
+      for (int b2 = 0; b2 < 2; b2++) {
+        const int b = 2 * pr + b2;
+        const bool b_active = step * 4 + b < count;
+        const bool b_tskip = (__ballot_sync(0xffffffffu, tskip) >> (8 * b)) & 1u;
+        uint32_t* out = reinterpret_cast<uint32_t*>(__shfl_sync(0xffffffffu, (unsigned long long)item.blk, 8 * b));
+        if (b_active && !b_tskip) out[(g * 8 + 2 * t) >> 1] = sat_pack16(d[2 * b2] >> 12, d[2 * b2 + 1] >> 12);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ---- n == 4: one lane per block -----------------------------------------------------------------------------
 __device__ __forceinline__ void idct4(const int (&x)[4], int (&y)[4]) {
   const int e0 = 64 * (x[0] + x[2]), e1 = 64 * (x[0] - x[2]);
@@ -428,7 +757,7 @@ __global__ void __launch_bounds__(256) transform4_kernel(Arenas A, int cls) {
       d[i] = min(32767, max(-32768, v));
     }
     int out[16];
-    if (tu_tskip(item.w, item.cidx)) {
+    if (item.tskip) {
 #pragma unroll
       for (int i = 0; i < 16; i++) out[i] = ((d[i] << 7) + 2048) >> 12;
     } else {
@@ -485,9 +814,17 @@ cudaError_t launch_transform(const Arenas& A, uint32_t max_tu_per_tile, int max_
   auto grid = [&](size_t max_steps, int resident) {
     return (unsigned)std::max<size_t>(1, std::min<size_t>((max_steps + kWarpsPerCta - 1) / kWarpsPerCta, (size_t)n_sm * resident));
   };
-  if (max_log2_tb >= 5) transform_kernel<32><<<grid(total / 64 + 1, 3), kWarpsPerCta * 32, 0, stream>>>(A, LIST_32);
-  if (max_log2_tb >= 4) transform_kernel<16><<<grid(total / 32 + 1, 4), kWarpsPerCta * 32, 0, stream>>>(A, LIST_16);
-  transform_kernel<8><<<grid(total / 16 + 1, 6), kWarpsPerCta * 32, 0, stream>>>(A, LIST_8);
+  // HEIC_B200_TRANSFORM_MMA=0: the register butterflies for 16x16 / 32x32 as well (A/B against the tensor-core form)
+  static const bool use_mma = []() { const char* e = getenv("HEIC_B200_TRANSFORM_MMA"); return !e || atoi(e) != 0; }();
+  if (use_mma) {
+    if (max_log2_tb >= 5) transform_mma_kernel<32><<<grid(total / 64 + 1, 4), kWarpsPerCta * 32, 0, stream>>>(A, LIST_32);
+    if (max_log2_tb >= 4) transform_mma_kernel<16><<<grid(total / 16 + 1, 8), kWarpsPerCta * 32, 0, stream>>>(A, LIST_16);
+  } else {
+    if (max_log2_tb >= 5) transform_kernel<32><<<grid(total / 64 + 1, 3), kWarpsPerCta * 32, 0, stream>>>(A, LIST_32);
+    if (max_log2_tb >= 4) transform_kernel<16><<<grid(total / 32 + 1, 4), kWarpsPerCta * 32, 0, stream>>>(A, LIST_16);
+  }
+  if (use_mma) transform_mma8_kernel<<<grid(total / 16 + 1, 8), kWarpsPerCta * 32, 0, stream>>>(A, LIST_8);
+  else transform_kernel<8><<<grid(total / 16 + 1, 6), kWarpsPerCta * 32, 0, stream>>>(A, LIST_8);
   transform4_kernel<true><<<grid(total / 32 + 1, 8), 256, 0, stream>>>(A, LIST_4Y);
   transform4_kernel<false><<<grid(total / 64 + 1, 8), 256, 0, stream>>>(A, LIST_4C);
   return cudaGetLastError();
