@@ -147,8 +147,33 @@ __device__ __forceinline__ bool filter_chroma_segment(uint32_t (&rw)[8][2], int 
   return true;
 }
 
+// 8x8 byte transpose of the packed cell (rw[r][h]: bytes 4h..4h+3 of row r), one 4x4 quadrant at a time: 8 PRMT each.
+__device__ __forceinline__ void transpose4(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+  const uint32_t t0 = __byte_perm(a, b, 0x5140), t1 = __byte_perm(c, d, 0x5140);  // a0 b0 a1 b1 | c0 d0 c1 d1
+  const uint32_t t2 = __byte_perm(a, b, 0x7362), t3 = __byte_perm(c, d, 0x7362);  // a2 b2 a3 b3 | c2 d2 c3 d3
+  o0 = __byte_perm(t0, t1, 0x5410);
+  o1 = __byte_perm(t0, t1, 0x7632);
+  o2 = __byte_perm(t2, t3, 0x5410);
+  o3 = __byte_perm(t2, t3, 0x7632);
+}
+__device__ __forceinline__ void transpose_cell(uint32_t (&rw)[8][2]) {
+  uint32_t t[8][2];
+  transpose4(rw[0][0], rw[1][0], rw[2][0], rw[3][0], t[0][0], t[1][0], t[2][0], t[3][0]);  // top-left stays
+  transpose4(rw[4][0], rw[5][0], rw[6][0], rw[7][0], t[0][1], t[1][1], t[2][1], t[3][1]);  // bottom-left -> top-right
+  transpose4(rw[0][1], rw[1][1], rw[2][1], rw[3][1], t[4][0], t[5][0], t[6][0], t[7][0]);  // top-right -> bottom-left
+  transpose4(rw[4][1], rw[5][1], rw[6][1], rw[7][1], t[4][1], t[5][1], t[6][1], t[7][1]);
+#pragma unroll
+  for (int r = 0; r < 8; r++) rw[r][0] = t[r][0], rw[r][1] = t[r][1];
+}
+
 // One shifted cell of plane CIDX.  (k, j): cell indices; the cell covers plane samples
 // [8k-4, 8k+4) x [8j-4, 8j+4) clipped to the picture.
+//
+// The four edge segments (vertical edge: rows 0..3, rows 4..7; then horizontal edge: columns 0..3, columns 4..7) run as
+// ONE rolled loop over a single copy of the metadata probes and of the filter: each iteration filters the segment that
+// lies in rows 0..3 across the vertical centre line, then swaps the cell's two halves; after the second iteration the cell
+// is transposed, so the horizontal edge's segments take the same form, and transposed back at the end.  Four inlined
+// copies of the filter (2.8 K instructions) made the kernel instruction-fetch bound (stall_no_instruction 3.4 per issue).
 template <int CIDX>
 __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int pitch, int pw, int ph, int k, int j,
                                              int beta_off2, int tc_off2, int c_qp_off) {
@@ -167,12 +192,11 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
       if (has_right) rw[r][1] = *reinterpret_cast<const uint32_t*>(row + x0 + 4);
     }
   }
-  // ---- which of the cell's four edge segments exist, and their QPs: all metadata loads issued before any filtering ----
   // vertical edge at x = 8k (luma: every 8 samples; chroma 4:2:0: every 8 chroma = 16 luma samples), segments of 4 rows;
   // horizontal edge at y = 8j, segments of 4 columns
   const int xe = (8 * k) << SUB, ye = (8 * j) << SUB;  // luma positions of the two edges
-  bool seg_do[4];
-  int seg_qp[4];  // qp_p + qp_q
+  // which of the four segments are transform-block edges, and their QPs: all metadata loads are issued before any filtering
+  uint32_t seg_do = 0, seg_qp = 0;  // bit g; byte g: qp_p + qp_q
 #pragma unroll
   for (int g = 0; g < 4; g++) {
     const bool vert = g < 2;
@@ -180,26 +204,30 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
     bool ok;
     if (vert) ok = has_left && has_right && (half == 0 ? has_top : has_bottom);
     else ok = has_top && has_bottom && (half == 0 ? has_left : has_right);
-    const int xl = vert ? xe : (x0 + 4 * half) << SUB, yl = vert ? (y0 + 4 * half) << SUB : ye;
-    seg_do[g] = false;
-    seg_qp[g] = 0;
     if (ok) {
-      seg_qp[g] = qp_at(pic, xl, yl) + (vert ? qp_at(pic, xl - 1, yl) : qp_at(pic, xl, yl - 1));
-      seg_do[g] = is_tu_edge(pic, xl, yl, vert ? xl : yl);
+      const int xl = vert ? xe : (x0 + 4 * half) << SUB, yl = vert ? (y0 + 4 * half) << SUB : ye;
+      seg_qp |= (uint32_t)(qp_at(pic, xl, yl) + (vert ? qp_at(pic, xl - 1, yl) : qp_at(pic, xl, yl - 1))) << (8 * g);
+      seg_do |= (is_tu_edge(pic, xl, yl, vert ? xl : yl) ? 1u : 0u) << g;
     }
   }
+  if (!seg_do) return;
   bool changed = false;
   // vertical edge first, then the horizontal edge on the vertically filtered samples (the order 8.7.2 prescribes)
+#pragma unroll 1
+  for (int g = 0; g < 4; g++) {
+    if ((seg_do >> g) & 1u) {
+      const int qp_sum = (int)((seg_qp >> (8 * g)) & 0xffu);
+      changed |= CIDX == 0 ? filter_luma_segment<true>(rw, 0, qp_sum, beta_off2, tc_off2)
+                           : filter_chroma_segment<true>(rw, 0, qp_sum, c_qp_off, tc_off2);
+    }
 #pragma unroll
-  for (int seg = 0; seg < 2; seg++)
-    if (seg_do[seg])
-      changed |= CIDX == 0 ? filter_luma_segment<true>(rw, seg, seg_qp[seg], beta_off2, tc_off2)
-                           : filter_chroma_segment<true>(rw, seg, seg_qp[seg], c_qp_off, tc_off2);
-#pragma unroll
-  for (int seg = 0; seg < 2; seg++)
-    if (seg_do[2 + seg])
-      changed |= CIDX == 0 ? filter_luma_segment<false>(rw, seg, seg_qp[2 + seg], beta_off2, tc_off2)
-                           : filter_chroma_segment<false>(rw, seg, seg_qp[2 + seg], c_qp_off, tc_off2);
+    for (int r = 0; r < 4; r++) {  // the other segment of this edge moves into rows 0..3 (and back after it)
+      uint32_t t0 = rw[r][0], t1 = rw[r][1];
+      rw[r][0] = rw[r + 4][0], rw[r][1] = rw[r + 4][1];
+      rw[r + 4][0] = t0, rw[r + 4][1] = t1;
+    }
+    if (g & 1) transpose_cell(rw);
+  }
   if (!changed) return;
 #pragma unroll
   for (int r = 0; r < 8; r++) {
