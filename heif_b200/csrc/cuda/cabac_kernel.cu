@@ -172,10 +172,11 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   const PicParams* pp = A.pics + tp->pic;
 
   Parser<TILES> P;
-  P.ctx_off = (uint32_t)(kCtaSharedBytes + ColdBytes<TILES>::value) + (uint32_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0u : (uint32_t)lane);
-  P.cold_off = (uint32_t)kCtaSharedBytes + (TILES == 32 ? threadIdx.x * 4u : (uint32_t)slot * 4u);
-  // keep the offsets in registers: left alone, ptxas rematerialises them from %tid (S2R + ALU ops) at every use
-  asm volatile("" : "+r"(P.ctx_off), "+r"(P.cold_off));
+  P.sm = (uint32_t)__cvta_generic_to_shared(smem_raw);
+  P.ctx_off = P.sm + (uint32_t)(kCtaSharedBytes + ColdBytes<TILES>::value) + (uint32_t)slot * NUM_CTX_PAD * TILES + (TILES == 1 ? 0u : (uint32_t)lane);
+  P.cold_off = P.sm + (uint32_t)kCtaSharedBytes + (TILES == 32 ? threadIdx.x * 4u : (uint32_t)slot * 4u);
+  // keep the addresses in registers: left alone, ptxas rematerialises them from %tid / SR_CgaCtaId (S2R + ALU ops) at every use
+  asm volatile("" : "+r"(P.sm), "+r"(P.ctx_off), "+r"(P.cold_off));
   P.cold(Parser<TILES>::CW_TILE) = (int)tile;
   P.e.data = A.bitstream + tp->bs_off;
   P.err = active ? 0 : -100;

@@ -66,9 +66,16 @@ HEIC_HD uint32_t compact1by1(uint32_t v) {  // even bits of an 8-bit z-order ind
 }
 
 #if defined(__CUDA_ARCH__)
-// All dynamically indexed parser state (tables, context tables) lives in the kernel's dynamic shared memory;
-// going through this symbol instead of generic pointers lets the compiler emit LDS/STS.
+// All dynamically indexed parser state (tables, context tables) lives in the kernel's dynamic shared memory.  The parser
+// reaches it through 32-bit shared-window addresses it carries in registers (Parser::sm, ctx_off, cold_off), turned into
+// pointers with smem_ptr(): the compiler still sees the shared address space and emits LDS/STS, but no longer forms the
+// address of the shared-memory symbol -- on sm_90+ that is S2UR SR_CgaCtaId + ULEA at the head of every out-of-line
+// routine, in front of its first load (3 % of the kernel's stall samples, 80 places).
 extern __shared__ __align__(16) unsigned char heic_cabac_smem[];
+template <class T>
+__device__ __forceinline__ T* smem_ptr(uint32_t addr) {
+  return reinterpret_cast<T*>(__cvta_shared_to_generic(addr));
+}
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -287,26 +294,26 @@ struct EngRet {
   uint32_t v;
   int bad;
 };
-static __device__ __noinline__ EngRet eng_decision(Engine e, uint32_t ctx_addr) {
-  uint32_t s = heic_cabac_smem[ctx_addr];
+static __device__ __noinline__ EngRet eng_decision(Engine e, uint32_t ctx_addr, uint32_t sm) {
+  uint32_t s = *smem_ptr<uint8_t>(ctx_addr);
   EngRet r;
-  r.v = (uint32_t)e.decision(reinterpret_cast<const CabacTabs*>(heic_cabac_smem), s);
-  heic_cabac_smem[ctx_addr] = (uint8_t)s;
+  r.v = (uint32_t)e.decision(smem_ptr<const CabacTabs>(sm), s);
+  *smem_ptr<uint8_t>(ctx_addr) = (uint8_t)s;
   r.e = e;
   r.bad = 0;
   return r;
 }
 // sig_coeff_flag of scan positions n_start .. 1 of one sub-block (9.3.4.2.5): context of position k = nibble k of `nib`,
 // entries `1 << stride_shift` bytes apart from ctx_addr.  One call per sub-block instead of one per bin.
-static __device__ __noinline__ EngRet eng_sig_run(Engine e, uint32_t ctx_addr, uint64_t nib, int n_start, int stride_shift) {
-  const CabacTabs* T = reinterpret_cast<const CabacTabs*>(heic_cabac_smem);
+static __device__ __noinline__ EngRet eng_sig_run(Engine e, uint32_t ctx_addr, uint64_t nib, int n_start, int stride_shift, uint32_t sm) {
+  const CabacTabs* T = smem_ptr<const CabacTabs>(sm);
   uint32_t sig = 0;
   HEIC_NO_UNROLL
   for (int k = n_start; k > 0; k--) {
     const uint32_t a = ctx_addr + ((uint32_t)((nib >> (4 * k)) & 15u) << stride_shift);
-    uint32_t s = heic_cabac_smem[a];
+    uint32_t s = *smem_ptr<uint8_t>(a);
     if (e.decision(T, s)) sig |= 1u << k;
-    heic_cabac_smem[a] = (uint8_t)s;
+    *smem_ptr<uint8_t>(a) = (uint8_t)s;
   }
   EngRet r;
   r.e = e;
@@ -316,8 +323,8 @@ static __device__ __noinline__ EngRet eng_sig_run(Engine e, uint32_t ctx_addr, u
 }
 // coeff_abs_level_greater1_flag of up to eight coefficients of a sub-block (9.3.4.2.6): ctx_addr is context 0 of the
 // sub-block's context set; returns the flags as a mask, greater1Ctx and the first position with the flag set in `bad`.
-static __device__ __noinline__ EngRet eng_gt1_run(Engine e, uint32_t ctx_addr, uint32_t sig, int stride_shift) {
-  const CabacTabs* T = reinterpret_cast<const CabacTabs*>(heic_cabac_smem);
+static __device__ __noinline__ EngRet eng_gt1_run(Engine e, uint32_t ctx_addr, uint32_t sig, int stride_shift, uint32_t sm) {
+  const CabacTabs* T = smem_ptr<const CabacTabs>(sm);
   uint32_t g1 = 0, m = sig;
   int greater1_ctx = 1, num = 0, last = -1;
   HEIC_NO_UNROLL
@@ -325,9 +332,9 @@ static __device__ __noinline__ EngRet eng_gt1_run(Engine e, uint32_t ctx_addr, u
     const int k = 31 - __clz(m);
     m &= ~(1u << k);
     const uint32_t a = ctx_addr + ((uint32_t)greater1_ctx << stride_shift);
-    uint32_t s = heic_cabac_smem[a];
+    uint32_t s = *smem_ptr<uint8_t>(a);
     const int f = e.decision(T, s);
-    heic_cabac_smem[a] = (uint8_t)s;
+    *smem_ptr<uint8_t>(a) = (uint8_t)s;
     num++;
     if (f) {
       g1 |= 1u << k;
@@ -411,9 +418,10 @@ struct Parser {
   enum { CW_TILE = 0, CW_QP_CODED, CW_QP_DELTA, CW_QP_Y, CW_QP_LAST, CW_QP_PRED, CW_QP_FIRST, CW_QG_X, CW_QG_Y, CW_COUNT };
 #if defined(__CUDA_ARCH__)
   static constexpr uint32_t kColdStride = STRIDE == 32 ? 1024u : 64u;  // bytes between a thread's cold words (threads with one x 4)
-  uint32_t cold_off;  // byte offset of this thread's first cold word
-  HEIC_HD int& cold(int j) const { return *reinterpret_cast<int*>(heic_cabac_smem + cold_off + (uint32_t)j * kColdStride); }
-  HEIC_HD const Arenas* arenas() const { return reinterpret_cast<const Arenas*>(heic_cabac_smem + kSmemArenasOff); }
+  uint32_t sm;        // shared-window address of the kernel's dynamic shared memory (tables at 0, arena pointers behind them)
+  uint32_t cold_off;  // shared-window address of this thread's first cold word
+  HEIC_HD int& cold(int j) const { return *smem_ptr<int>(cold_off + (uint32_t)j * kColdStride); }
+  HEIC_HD const Arenas* arenas() const { return smem_ptr<const Arenas>(sm + kSmemArenasOff); }
   HEIC_HD const TileParams* TP() const { return arenas()->tiles + (uint32_t)cold(CW_TILE); }
   HEIC_HD const PicParams* PP() const { return arenas()->pics + TP()->pic; }
   HEIC_HD uint32_t* tu_map_p() const { return arenas()->tu_map + TP()->tu_off; }
@@ -453,10 +461,10 @@ struct Parser {
   HEIC_HD int& qg_y() { return cold(CW_QG_Y); }
 
 #if defined(__CUDA_ARCH__)
-  uint32_t ctx_off;  // byte offset of this thread's context table in the kernel's dynamic shared memory
-  HEIC_HD const CabacTabs* tabs() const { return reinterpret_cast<const CabacTabs*>(heic_cabac_smem); }
-  HEIC_HD uint32_t ld_ctx(int idx) const { return heic_cabac_smem[ctx_off + idx * STRIDE]; }
-  HEIC_HD void st_ctx(int idx, uint32_t v) { heic_cabac_smem[ctx_off + idx * STRIDE] = (uint8_t)v; }
+  uint32_t ctx_off;  // shared-window address of this thread's context table
+  HEIC_HD const CabacTabs* tabs() const { return smem_ptr<const CabacTabs>(sm); }
+  HEIC_HD uint32_t ld_ctx(int idx) const { return *smem_ptr<uint8_t>(ctx_off + idx * STRIDE); }
+  HEIC_HD void st_ctx(int idx, uint32_t v) { *smem_ptr<uint8_t>(ctx_off + idx * STRIDE) = (uint8_t)v; }
 #else
   HEIC_HD const CabacTabs* tabs() const { return T; }
   HEIC_HD uint32_t ld_ctx(int idx) const { return ctx[idx * STRIDE]; }
@@ -464,7 +472,7 @@ struct Parser {
 #endif
   HEIC_HD int dec(int idx) {
 #if defined(HEIC_CABAC_OUTLINED)
-    const EngRet r = eng_decision(e, ctx_off + idx * STRIDE);
+    const EngRet r = eng_decision(e, ctx_off + idx * STRIDE, sm);
     e = r.e;
     return (int)r.v;
 #else
@@ -486,7 +494,7 @@ struct Parser {
   // bypass-coded elements
 #if defined(HEIC_CABAC_OUTLINED)
   HEIC_HD uint32_t sig_run(int add, uint64_t nib, int n_start) {
-    const EngRet r = eng_sig_run(e, ctx_off + add * STRIDE, nib, n_start, STRIDE == 32 ? 5 : 0);
+    const EngRet r = eng_sig_run(e, ctx_off + add * STRIDE, nib, n_start, STRIDE == 32 ? 5 : 0, sm);
     e = r.e;
     return r.v;
   }
@@ -767,7 +775,7 @@ HEIC_NO_UNROLL
     const int first_sig = 31 - HEIC_CLZ(sig & (0u - sig));
 #if defined(HEIC_CABAC_OUTLINED)
     {
-      const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0);
+      const EngRet r = eng_gt1_run(e, ctx_off + (CTX_GT1 + (c_idx ? 16 : 0) + (ctx_set << 2)) * STRIDE, sig, STRIDE == 32 ? 5 : 0, sm);
       e = r.e;
       g1 = r.v & 0xffffu;
       beyond8 = r.v >> 16;
