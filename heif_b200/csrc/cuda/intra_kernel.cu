@@ -36,17 +36,32 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// A pointer into the kernel's dynamic shared memory kept as its 32-bit shared-window address.  Converting to a C++
+// pointer at the point of use keeps the address space visible to the compiler (LDS/STS) while every address derives from
+// ONE register-held base: as 64-bit generic pointers the nine of them were re-formed from the symbol's address
+// (S2UR SR_CgaCtaId + ULEA, 49 places in the kernel) wherever the register allocator had dropped them.
+template <class T>
+struct SP {
+  uint32_t a;
+  __device__ __forceinline__ operator T*() const { return reinterpret_cast<T*>(__cvta_shared_to_generic(a)); }
+  __device__ __forceinline__ T& operator[](int i) const { return reinterpret_cast<T*>(__cvta_shared_to_generic(a))[i]; }
+  __device__ __forceinline__ SP operator+(int i) const { return SP{a + (uint32_t)(i * (int)sizeof(T))}; }
+  __device__ __forceinline__ int operator-(SP o) const { return (int)(a - o.a) / (int)sizeof(T); }
+};
 struct Ctu {
   int w, h, ctb, ctb4, x_ctb, y_ctb;
-  uint8_t* buf[3];   // sample (x, y) relative to the CTU origin at buf[(y + 1) * stride + x + 16], x, y >= -1
+  SP<uint8_t> buf[3];   // sample (x, y) relative to the CTU origin at buf[(y + 1) * stride + x + 16], x, y >= -1
   int stride[3];
-  uint8_t* ref;      // reference samples after substitution, s = 0 .. 4n (bottom-left -> corner -> top-right);
-                     // the second block of a chroma pair (or the smoothed luma samples) at ref + kRefSpan
-  uint8_t* refa;     // angular reference array, refa[-32 .. 64]; second block of a pair at refa + kRefaSpan
-  int16_t* res[3];   // residuals of this CTU, z-ordered as in the coefficient arena
-  uint32_t* tuw;     // tu_map words of this CTU
+  SP<uint8_t> ref;      // reference samples after substitution, s = 0 .. 4n (bottom-left -> corner -> top-right);
+                        // the second block of a chroma pair (or the smoothed luma samples) at ref + kRefSpan
+  SP<uint8_t> refa;     // angular reference array, refa[-32 .. 64]; second block of a pair at refa + kRefaSpan
+  SP<int16_t> res[3];   // residuals of this CTU, z-ordered as in the coefficient arena
+  SP<uint32_t> tuw;     // tu_map words of this CTU
   int lane;
   int strong_flag;
 };
@@ -360,16 +375,17 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
   {
     uint32_t wbase = (uint32_t)progress_bytes + (uint32_t)slot * (uint32_t)L.warp_bytes;
     asm volatile("" : "+r"(wbase));  // opaque: keeps the warp's base offset in a register instead of re-deriving it per use
-    unsigned char* p = smem_raw + wbase;
-    c.res[0] = reinterpret_cast<int16_t*>(p);
-    c.res[1] = reinterpret_cast<int16_t*>(p + L.res1);
-    c.res[2] = reinterpret_cast<int16_t*>(p + L.res2);
-    c.tuw = reinterpret_cast<uint32_t*>(p + L.tuw);
-    c.ref = p + L.ref;
-    c.refa = p + L.refa + 32;
-    c.buf[0] = p + L.buf0;
-    c.buf[1] = p + L.buf1;
-    c.buf[2] = p + L.buf2;
+    uint32_t p = (uint32_t)__cvta_generic_to_shared(smem_raw) + wbase;
+    asm volatile("" : "+r"(p));  // the one register every shared-memory address of this warp derives from
+    c.res[0].a = p;
+    c.res[1].a = p + (uint32_t)L.res1;
+    c.res[2].a = p + (uint32_t)L.res2;
+    c.tuw.a = p + (uint32_t)L.tuw;
+    c.ref.a = p + (uint32_t)L.ref;
+    c.refa.a = p + (uint32_t)L.refa + 32u;
+    c.buf[0].a = p + (uint32_t)L.buf0;
+    c.buf[1].a = p + (uint32_t)L.buf1;
+    c.buf[2].a = p + (uint32_t)L.buf2;
     c.stride[0] = L.stride_y;
     c.stride[1] = c.stride[2] = L.stride_c;
   }
@@ -383,17 +399,17 @@ __global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas 
       // ---- stage this CTU's residuals and tu_map words (contiguous in HBM) ------------------------------
       {
         const char* g0 = reinterpret_cast<const char*>(A.coeff + tp->coeff_off[0] + (size_t)ctb_addr * n4sq * 16);
-        for (int i = lane * 16; i < n4sq * 32; i += 512) cp_async16(reinterpret_cast<char*>(c.res[0]) + i, g0 + i);
+        for (int i = lane * 16; i < n4sq * 32; i += 512) cp_async16s(c.res[0].a + i, g0 + i);
         if (n_planes == 3) {
           const char* g1 = reinterpret_cast<const char*>(A.coeff + tp->coeff_off[1] + (size_t)ctb_addr * n4sq * 4);
           const char* g2 = reinterpret_cast<const char*>(A.coeff + tp->coeff_off[2] + (size_t)ctb_addr * n4sq * 4);
           for (int i = lane * 16; i < n4sq * 8; i += 512) {
-            cp_async16(reinterpret_cast<char*>(c.res[1]) + i, g1 + i);
-            cp_async16(reinterpret_cast<char*>(c.res[2]) + i, g2 + i);
+            cp_async16s(c.res[1].a + i, g1 + i);
+            cp_async16s(c.res[2].a + i, g2 + i);
           }
         }
         const char* gt = reinterpret_cast<const char*>(tu_map + (size_t)ctb_addr * n4sq);
-        for (int i = lane * 16; i < n4sq * 4; i += 512) cp_async16(reinterpret_cast<char*>(c.tuw) + i, gt + i);
+        for (int i = lane * 16; i < n4sq * 4; i += 512) cp_async16s(c.tuw.a + i, gt + i);
       }
       if (n_slots > 1 && ry > 0) {
         const int need = min(rx + 2, wctb);
