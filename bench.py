@@ -465,7 +465,7 @@ def main():
                     raise SystemExit(f"decode_grids, image {int(i)}: RGB differs from the oracle")
     pixel_check["e2e_images_checked"] = [int(i) for i in chk if i < eb]
     barrier()
-    e2e_steps = max(10, min(args.steps, 16))  # enough calls that the pipeline's fill and drain are amortised
+    e2e_steps = max(12, min(args.steps, 32))  # enough calls that the pipeline's fill and drain are amortised
     t0 = time.perf_counter()
     jobs = []
     submit_s = 0.0

@@ -177,7 +177,10 @@ __global__ void __launch_bounds__(TILES == 32 ? 256 : 512, TILES == 32 ? HEIC_CA
   P.cold_off = P.sm + (uint32_t)kCtaSharedBytes + (TILES == 32 ? threadIdx.x * 4u : (uint32_t)slot * 4u);
   // keep the addresses in registers: left alone, ptxas rematerialises them from %tid / SR_CgaCtaId (S2R + ALU ops) at every use
   asm volatile("" : "+r"(P.sm), "+r"(P.ctx_off), "+r"(P.cold_off));
-  P.cold(Parser<TILES>::CW_TILE) = (int)tile;
+  P.cold(Parser<TILES>::CW_TP_LO) = (int)(uint32_t)(unsigned long long)tp;
+  P.cold(Parser<TILES>::CW_TP_HI) = (int)(uint32_t)((unsigned long long)tp >> 32);
+  P.cold(Parser<TILES>::CW_PP_LO) = (int)(uint32_t)(unsigned long long)pp;
+  P.cold(Parser<TILES>::CW_PP_HI) = (int)(uint32_t)((unsigned long long)pp >> 32);
   P.e.data = A.bitstream + tp->bs_off;
   P.err = active ? 0 : -100;
 

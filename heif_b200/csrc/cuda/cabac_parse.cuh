@@ -111,7 +111,7 @@ struct Engine {
   // load's latency (4 % of the kernel's stall samples).
   HEIC_HD uint32_t load16_raw(uint32_t p) const {  // p even
 #if defined(__CUDA_ARCH__)
-    return p < end ? (uint32_t)*reinterpret_cast<const uint16_t*>(data + p) : 0u;
+    return p < end ? (uint32_t)__ldg(reinterpret_cast<const uint16_t*>(data + p)) : 0u;
 #else
     return load16(p);
 #endif
@@ -415,15 +415,21 @@ struct Parser {
   // and the QP state in per-thread words, the arena bases once per CTA), NOT in registers: held in registers it cost 28 of
   // them for the whole kernel, and the register file is what bounds the CABAC kernel's occupancy (4 CTAs per SM at 64
   // registers against 3 at 80).  On the host (tests/emul, tests/synth, tests/fuzz) they are plain members.
-  enum { CW_TILE = 0, CW_QP_CODED, CW_QP_DELTA, CW_QP_Y, CW_QP_LAST, CW_QP_PRED, CW_QP_FIRST, CW_QG_X, CW_QG_Y, CW_COUNT };
+  enum { CW_TP_LO = 0, CW_TP_HI, CW_PP_LO, CW_PP_HI, CW_QP_CODED, CW_QP_DELTA, CW_QP_Y, CW_QP_LAST, CW_QP_PRED, CW_QP_FIRST, CW_QG_X, CW_QG_Y, CW_COUNT };
 #if defined(__CUDA_ARCH__)
   static constexpr uint32_t kColdStride = STRIDE == 32 ? 1024u : 64u;  // bytes between a thread's cold words (threads with one x 4)
   uint32_t sm;        // shared-window address of the kernel's dynamic shared memory (tables at 0, arena pointers behind them)
   uint32_t cold_off;  // shared-window address of this thread's first cold word
   HEIC_HD int& cold(int j) const { return *smem_ptr<int>(cold_off + (uint32_t)j * kColdStride); }
   HEIC_HD const Arenas* arenas() const { return smem_ptr<const Arenas>(sm + kSmemArenasOff); }
-  HEIC_HD const TileParams* TP() const { return arenas()->tiles + (uint32_t)cold(CW_TILE); }
-  HEIC_HD const PicParams* PP() const { return arenas()->pics + TP()->pic; }
+  // the tile's and its picture's parameter structures: pointers in the thread's cold words (two independent LDS each, instead
+  // of the chain arena pointer -> tile index -> tiles[tile].pic -> pics[pic] through global memory)
+  HEIC_HD const TileParams* TP() const {
+    return reinterpret_cast<const TileParams*>((unsigned long long)(uint32_t)cold(CW_TP_LO) | ((unsigned long long)(uint32_t)cold(CW_TP_HI) << 32));
+  }
+  HEIC_HD const PicParams* PP() const {
+    return reinterpret_cast<const PicParams*>((unsigned long long)(uint32_t)cold(CW_PP_LO) | ((unsigned long long)(uint32_t)cold(CW_PP_HI) << 32));
+  }
   HEIC_HD uint32_t* tu_map_p() const { return arenas()->tu_map + TP()->tu_off; }
   HEIC_HD int16_t* coeff_p(int c) const { return arenas()->coeff + TP()->coeff_off[c]; }
   HEIC_HD uint8_t* ipm_p() const { return arenas()->ipm + TP()->map4_off; }
