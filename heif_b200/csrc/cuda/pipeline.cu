@@ -126,6 +126,9 @@ struct heic_b200_ctx {
   int pipe_chunk = 0;   // images per chunk; 0: automatic (see submit_grids)
   int pipe_slots = 0;   // chunks in flight; 0: automatic
   cudaEvent_t trace_base = nullptr;  // HEIC_B200_TRACE=2: time zero of the chunk timelines
+  int pipe_order = 1;                // chunks in flight keep their order on the device (HEIC_B200_PIPE_ORDER=0: A/B)
+  cudaEvent_t ev_cabac = nullptr, ev_d2h = nullptr;  // end of the last queued chunk's CABAC stage / device->host copies
+  bool d2h_recorded = false;
   cudaStream_t pipe_stream[kPipe] = {};
   std::unique_ptr<heic_b200_batch> pipe_batch[kPipe];
   PipePending pipe_pending[kPipe];
@@ -201,6 +204,8 @@ struct heic_b200_batch {
 
 heic_b200_ctx::~heic_b200_ctx() {
   if (trace_base) cudaEventDestroy(trace_base);
+  if (ev_cabac) cudaEventDestroy(ev_cabac);
+  if (ev_d2h) cudaEventDestroy(ev_d2h);
   for (int i = 0; i < kPipe; i++) {
     for (cudaEvent_t e : pipe_pending[i].ev)
       if (e) cudaEventDestroy(e);
@@ -678,6 +683,7 @@ int32_t heic_b200_create(int32_t device, heic_b200_ctx** out_ctx) {
     c->cabac_plain_sort = env_int("HEIC_B200_CABAC_PLAIN_SORT", 0) != 0;
     c->cabac_group_cap_pct = std::max(0, env_int("HEIC_B200_CABAC_GROUP_CAP", 0));
     c->pipe_slots = std::min((int)heic_b200_ctx::kPipe, std::max(0, env_int("HEIC_B200_PIPE_SLOTS", 0)));
+    c->pipe_order = env_int("HEIC_B200_PIPE_ORDER", 1) != 0;
     *out_ctx = c.release();
     return 0;
   }));
@@ -973,13 +979,26 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
       // the columns that matter are when CABAC, the other kernels and the D2H copy of this chunk END)
       CU(cudaEventRecord(pend.ev[0], st));
       CU(cudaEventRecord(pend.ev[1], st));
-      b->run(HEIC_STAGE_CABAC);
-      CU(cudaEventRecord(pend.ev[2], st));
-      b->run((rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR)) & ~HEIC_STAGE_CABAC);
-      CU(cudaEventRecord(pend.ev[3], st));
-    } else {
-      b->run(rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR));
     }
+    // Chunks in flight are kept in order on the device: a chunk's CABAC stage starts when the previous chunk's has ended
+    // (so CABAC of chunk k+1 shares the GPU with the throughput kernels of chunk k, not with another latency-bound CABAC
+    // stage), and its device->host copy starts when the previous chunk's has ended (each copy gets the whole link).  Left to
+    // the hardware scheduler, the first chunk of a run took 390 ms to reach its copy instead of 140 (three chunks' kernels
+    // interleaved) and the copy engine idled that long.
+    if (ctx->pipe_order) {
+      if (!ctx->ev_cabac) {
+        CU(cudaEventCreateWithFlags(&ctx->ev_cabac, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->ev_d2h, cudaEventDisableTiming));
+      } else {
+        CU(cudaStreamWaitEvent(st, ctx->ev_cabac, 0));
+      }
+    }
+    b->run(HEIC_STAGE_CABAC);
+    if (ctx->pipe_order) CU(cudaEventRecord(ctx->ev_cabac, st));
+    if (trace2) CU(cudaEventRecord(pend.ev[2], st));
+    b->run((rgb_out ? HEIC_STAGE_ALL : (HEIC_STAGE_ALL & ~HEIC_STAGE_COLOR)) & ~HEIC_STAGE_CABAC);
+    if (trace2) CU(cudaEventRecord(pend.ev[3], st));
+    if (ctx->pipe_order && ctx->d2h_recorded) CU(cudaStreamWaitEvent(st, ctx->ev_d2h, 0));
     t_run += ms_since(t0);
     if (rgb_out) {
       bool one_copy = image_stride == b->rgb_image_stride && pitch == b->rgb_pitch;
@@ -1020,6 +1039,10 @@ static heic_b200_job* submit_grids(heic_b200_ctx* ctx, const heic_image_desc* im
       }
     }
     CU(cudaMemcpyAsync(b->h_status.p, b->d_status.p, b->tiles.size() * sizeof(TileStatusDev), cudaMemcpyDeviceToHost, st));
+    if (ctx->pipe_order) {
+      CU(cudaEventRecord(ctx->ev_d2h, st));
+      ctx->d2h_recorded = true;
+    }
     if (trace2) CU(cudaEventRecord(pend.ev[4], st));
     ctx->pipe_pending[slot].job = job.get();
     ctx->pipe_pending[slot].tile0 = first_tile[i0];
