@@ -1,11 +1,12 @@
-"""Digest the round's ncu artefacts into profiles/:  python tools/profile_digest.py <launches.csv> <ncu_full_summary.txt> <n_images> [first_n_launches]
- - profiles/r01_final_launches_summary.txt : per-kernel mean launch time and share of one decode
+"""Digest the round's ncu artefacts into profiles/:  python tools/profile_digest.py <launches.csv> <ncu_full_summary.txt> <n_images> [first_n_launches] [prefix]
+ - profiles/<prefix>_launches_summary.txt : per-kernel mean launch time and share of one decode
  - profiles/dram_traffic_per_image.json    : dram__bytes_read.sum + dram__bytes_write.sum per stage and image (bench.py `traffic`)"""
 import collections, csv, json, os, re, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 launches, full, n_img = sys.argv[1], sys.argv[2], int(sys.argv[3])
 first = int(sys.argv[4]) if len(sys.argv) > 4 else 0  # only the first `first` launches (the resident-batch decodes)
+prefix = sys.argv[5] if len(sys.argv) > 5 else "r02_final"  # profiles/<prefix>_launches_summary.txt
 
 rows = list(csv.reader(open(launches)))
 h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -28,7 +29,7 @@ for r in rows[h + 1:]:
     t[name].append(v)
 n_dec = min(len(v) for v in t.values())
 per_dec = sum(sum(v) / len(v) * (len(v) // n_dec) for v in t.values())
-with open(os.path.join(ROOT, "profiles", "r01_final_launches_summary.txt"), "w") as f:
+with open(os.path.join(ROOT, "profiles", prefix + "_launches_summary.txt"), "w") as f:
     f.write(f"# ncu launch list, `python bench.py --steps 2 --warmup 3 --no-cpu` (batch {n_img} images/GPU), first {n_dec} full decodes\n")
     f.write("# gpu__time_duration.sum per launch, --clock-control none; serialised + cold cache: compare SHARES with bench.py's `stages`, not absolutes\n")
     f.write(f"# {per_dec:.1f} ms per decode under ncu\n\n")
@@ -57,11 +58,11 @@ for b in open(full).read().split("----"):
         missing.append(m.group(1).strip()[:50])
     else:
         traffic[stage] += tot
-out = {"_source": f"ncu --set full, profiles/r01_final_ncu_full_summary.txt (bench.py --steps 2 --warmup 3 --no-cpu, batch {n_img}): "
+out = {"_source": f"ncu --set full, profiles/{prefix}_ncu_full_summary.txt (tools/profile_batch.py --decodes 1, batch {n_img}): "
                   f"dram__bytes_read.sum + dram__bytes_write.sum per launch / {n_img} images, summed per stage",
        "_not_captured": missing}
 for s, v in traffic.items():
     out[s] = v / n_img
 json.dump(out, open(os.path.join(ROOT, "profiles", "dram_traffic_per_image.json"), "w"), indent=1)
-print(open(os.path.join(ROOT, "profiles", "r01_final_launches_summary.txt")).read())
+print(open(os.path.join(ROOT, "profiles", prefix + "_launches_summary.txt")).read())
 print(json.dumps(out, indent=1))
