@@ -76,12 +76,15 @@ struct SmemSync {
         if (ns < 2048) ns *= 2;
       }
     } else {
+      // The whole warp polls (one broadcast load) and yields together.  Measured on this pool's B200s a NANOSLEEP returns
+      // after ~20 ns whatever its argument (10.9 G of them for 200 warp-seconds of waiting), so the back-off is a run of
+      // them per progress probe, not a growing argument.  The poll instructions are not what bounds the kernel: halving
+      // them changed nothing, and an mbarrier-suspended wait measured slower.
       __syncwarp();
-      if (lane == 0)
-        while (pr[row] < base + n) {
-          __nanosleep(ns);
-          if (ns < 2048) ns *= 2;
-        }
+      while (pr[row] < base + n) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) __nanosleep(2048);
+      }
       __syncwarp();
     }
     __threadfence_block();
