@@ -58,91 +58,95 @@ __device__ __forceinline__ bool is_tu_edge(const Pic& p, int x, int y, int pos) 
 }
 __device__ __forceinline__ int qp_at(const Pic& p, int x, int y) { return p.qp_map[(y >> 3) * p.w8 + (x >> 3)]; }
 
-// ---- the cell stays PACKED (rw[r][0] = samples 0..3 of row r, rw[r][1] = samples 4..7) and only the lines an edge
-// segment really filters are unpacked: a segment that is no transform-block edge, or whose decisions (taken on its first
-// and last line, 8.7.2.5.3) say "leave it", costs no unpacking and no repacking, and the unpacked cell (64 registers) never
-// exists.  Line l of a vertical-edge segment s is row 4s + l (p3..p0 = left word, q0..q3 = right word); line l of a
-// horizontal-edge segment s is column 4s + l (byte l of word s of rows 0..7).
-template <bool VERT>
-__device__ __forceinline__ void get_line(const uint32_t (&rw)[8][2], int s, int l, int (&v)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; i++)
-    v[i] = VERT ? (int)((rw[4 * s + l][i >> 2] >> (8 * (i & 3))) & 0xffu) : (int)((rw[i][s] >> (8 * l)) & 0xffu);
+// ---- the cell stays PACKED: rw[r][0] = samples 0..3 of row r (p3 p2 p1 p0 of the line across the vertical centre line),
+// rw[r][1] = samples 4..7 (q0 q1 q2 q3).  Every quantity of 8.7.2.5.3 / 8.7.2.5.7 is a small-integer linear form of the eight
+// samples of a line, so it is evaluated ON THE PACKED WORDS with two `dp4a.u32.s32` (unsigned samples x signed byte
+// weights; the integer-multiplier pipe, which these kernels otherwise leave half idle) -- no unpacking.  And a filtered
+// sample replaces the old one by ADDING its difference at the byte's position (three IMADs per word): every new sample is
+// a clipped value in 0..255, so the sum of the per-byte differences never carries from one byte into the next -- no
+// repacking either.  Line l of the segment the loop presents is row l (the loop swaps halves / transposes the cell so that
+// all four segments of a cell take this form).
+__device__ __forceinline__ int dp4(uint32_t samples, uint32_t weights, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(samples), "r"(weights), "r"(acc));
+  return d;
 }
-// writes back samples 1..6 of the line (p2 p1 p0 q0 q1 q2: all a filter can change)
-template <bool VERT>
-__device__ __forceinline__ void put_line(uint32_t (&rw)[8][2], int s, int l, const int (&v)[8]) {
-  if (VERT) {
-    rw[4 * s + l][0] = (rw[4 * s + l][0] & 0x000000ffu) | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-    rw[4 * s + l][1] = (rw[4 * s + l][1] & 0xff000000u) | (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16);
-  } else {
-#pragma unroll
-    for (int i = 1; i < 7; i++) rw[i][s] = (rw[i][s] & ~(0xffu << (8 * l))) | ((uint32_t)v[i] << (8 * l));
-  }
+// signed byte weights of (byte 0, byte 1, byte 2, byte 3) = (p3, p2, p1, p0) of the left word, (q0, q1, q2, q3) of the right one
+__host__ __device__ constexpr uint32_t W(int a, int b, int c, int d) {
+  return ((uint32_t)a & 0xffu) | (((uint32_t)b & 0xffu) << 8) | (((uint32_t)c & 0xffu) << 16) | (((uint32_t)d & 0xffu) << 24);
 }
+// P.w1 + Q.w2 + c
+__device__ __forceinline__ int lin(uint32_t P, uint32_t Q, uint32_t wp, uint32_t wq, int c) { return dp4(Q, wq, dp4(P, wp, c)); }
 
-// 8.7.2.5.3 decisions + 8.7.2.5.7 filters of one luma edge segment.  Returns whether anything changed.
-template <bool VERT>
-__device__ __forceinline__ bool filter_luma_segment(uint32_t (&rw)[8][2], int seg, int qp_sum, int beta_off2, int tc_off2) {
+// 8.7.2.5.3 decisions + 8.7.2.5.7 filters of the luma edge segment in rows 0..3.  Returns whether anything changed.
+__device__ __forceinline__ bool filter_luma_segment(uint32_t (&rw)[8][2], int qp_sum, int beta_off2, int tc_off2) {
   const int qpl = (qp_sum + 1) >> 1;
   const int beta = kBetaTable[clip3(0, 51, qpl + beta_off2)];
   const int tc = kTcTable[clip3(0, 53, qpl + 2 + tc_off2)];
-  int s[4][8];
-  get_line<VERT>(rw, seg, 0, s[0]);
-  get_line<VERT>(rw, seg, 3, s[3]);
-  const int dp0 = abs(s[0][1] - 2 * s[0][2] + s[0][3]), dp3 = abs(s[3][1] - 2 * s[3][2] + s[3][3]);
-  const int dq0 = abs(s[0][6] - 2 * s[0][5] + s[0][4]), dq3 = abs(s[3][6] - 2 * s[3][5] + s[3][4]);
+  const uint32_t P0 = rw[0][0], Q0 = rw[0][1], P3 = rw[3][0], Q3 = rw[3][1];
+  const int dp0 = abs(dp4(P0, W(0, 1, -2, 1), 0)), dp3 = abs(dp4(P3, W(0, 1, -2, 1), 0));
+  const int dq0 = abs(dp4(Q0, W(1, -2, 1, 0), 0)), dq3 = abs(dp4(Q3, W(1, -2, 1, 0), 0));
   const int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3;
   if (dpq0 + dpq3 >= beta) return false;
-  const bool s0 = 2 * dpq0 < (beta >> 2) && abs(s[0][0] - s[0][3]) + abs(s[0][4] - s[0][7]) < (beta >> 3) &&
-                  abs(s[0][3] - s[0][4]) < ((5 * tc + 1) >> 1);
-  const bool s3 = 2 * dpq3 < (beta >> 2) && abs(s[3][0] - s[3][3]) + abs(s[3][4] - s[3][7]) < (beta >> 3) &&
-                  abs(s[3][3] - s[3][4]) < ((5 * tc + 1) >> 1);
+  const int tc25 = (5 * tc + 1) >> 1;
+  const bool s0 = 2 * dpq0 < (beta >> 2) && abs(dp4(P0, W(1, 0, 0, -1), 0)) + abs(dp4(Q0, W(1, 0, 0, -1), 0)) < (beta >> 3) &&
+                  abs(lin(P0, Q0, W(0, 0, 0, 1), W(-1, 0, 0, 0), 0)) < tc25;
+  const bool s3 = 2 * dpq3 < (beta >> 2) && abs(dp4(P3, W(1, 0, 0, -1), 0)) + abs(dp4(Q3, W(1, 0, 0, -1), 0)) < (beta >> 3) &&
+                  abs(lin(P3, Q3, W(0, 0, 0, 1), W(-1, 0, 0, 0), 0)) < tc25;
   const bool strong = s0 && s3;
   const bool dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
-  get_line<VERT>(rw, seg, 1, s[1]);
-  get_line<VERT>(rw, seg, 2, s[2]);
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    const int p3 = s[l][0], p2 = s[l][1], p1 = s[l][2], p0 = s[l][3];
-    const int q0 = s[l][4], q1 = s[l][5], q2 = s[l][6], q3 = s[l][7];
+    const uint32_t P = rw[l][0], Q = rw[l][1];
     if (strong) {
-      s[l][3] = clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
-      s[l][2] = clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
-      s[l][1] = clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
-      s[l][4] = clip3(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
-      s[l][5] = clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
-      s[l][6] = clip3(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+      // new - old of p0 p1 p2 q0 q1 q2: the old sample, times the divisor, is folded into the weights (the shift is exact on
+      // it), then clipped to +-2tc
+      const int t2 = 2 * tc;
+      const int e_p0 = clip3(-t2, t2, lin(P, Q, W(0, 1, 2, 2 - 8), W(2, 1, 0, 0), 4) >> 3);
+      const int e_p1 = clip3(-t2, t2, lin(P, Q, W(0, 1, 1 - 4, 1), W(1, 0, 0, 0), 2) >> 2);
+      const int e_p2 = clip3(-t2, t2, lin(P, Q, W(2, 3 - 8, 1, 1), W(1, 0, 0, 0), 4) >> 3);
+      const int e_q0 = clip3(-t2, t2, lin(P, Q, W(0, 0, 1, 2), W(2 - 8, 2, 1, 0), 4) >> 3);
+      const int e_q1 = clip3(-t2, t2, lin(P, Q, W(0, 0, 0, 1), W(1, 1 - 4, 1, 0), 2) >> 2);
+      const int e_q2 = clip3(-t2, t2, lin(P, Q, W(0, 0, 0, 1), W(1, 1, 3 - 8, 2), 4) >> 3);
+      rw[l][0] = P + (uint32_t)e_p2 * 256u + (uint32_t)e_p1 * 65536u + (uint32_t)e_p0 * 16777216u;
+      rw[l][1] = Q + (uint32_t)e_q0 + (uint32_t)e_q1 * 256u + (uint32_t)e_q2 * 65536u;
     } else {
-      int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+      int delta = lin(P, Q, W(0, 0, 3, -9), W(9, -3, 0, 0), 8) >> 4;
       if (abs(delta) < tc * 10) {
         delta = clip3(-tc, tc, delta);
-        s[l][3] = clip8(p0 + delta);
-        s[l][4] = clip8(q0 - delta);
-        if (dep) s[l][2] = clip8(p1 + clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
-        if (deq) s[l][5] = clip8(q1 + clip3(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+        const int p0 = dp4(P, W(0, 0, 0, 1), 0), q0 = dp4(Q, W(1, 0, 0, 0), 0);
+        const int ep = clip8(p0 + delta) - p0, eq = clip8(q0 - delta) - q0;
+        uint32_t addp = (uint32_t)ep * 16777216u, addq = (uint32_t)eq;
+        if (dep) {
+          const int p1 = dp4(P, W(0, 0, 1, 0), 0);
+          const int e = clip3(-(tc >> 1), tc >> 1, (((dp4(P, W(0, 1, 0, 1), 1) >> 1) - p1 + delta) >> 1));
+          addp += (uint32_t)(clip8(p1 + e) - p1) * 65536u;
+        }
+        if (deq) {
+          const int q1 = dp4(Q, W(0, 1, 0, 0), 0);
+          const int e = clip3(-(tc >> 1), tc >> 1, (((dp4(Q, W(1, 0, 1, 0), 1) >> 1) - q1 - delta) >> 1));
+          addq += (uint32_t)(clip8(q1 + e) - q1) * 256u;
+        }
+        rw[l][0] = P + addp;
+        rw[l][1] = Q + addq;
       }
     }
-    put_line<VERT>(rw, seg, l, s[l]);
   }
   return true;
 }
 
-template <bool VERT>
-__device__ __forceinline__ bool filter_chroma_segment(uint32_t (&rw)[8][2], int seg, int qp_sum, int c_qp_off, int tc_off2) {
+__device__ __forceinline__ bool filter_chroma_segment(uint32_t (&rw)[8][2], int qp_sum, int c_qp_off, int tc_off2) {
   const int qpi = ((qp_sum + 1) >> 1) + c_qp_off;  // cQpPicOffset: PPS offset only (8.7.2.5.5)
   const int qpc = qpi < 30 ? qpi : (qpi >= 43 ? qpi - 6 : kChromaQp[qpi - 30]);
   const int tc = kTcTable[clip3(0, 53, qpc + 2 + tc_off2)];
   if (!tc) return false;
 #pragma unroll
   for (int l = 0; l < 4; l++) {
-    int v[8];
-    get_line<VERT>(rw, seg, l, v);
-    const int p1 = v[2], p0 = v[3], q0 = v[4], q1 = v[5];
-    const int delta = clip3(-tc, tc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
-    v[3] = clip8(p0 + delta);
-    v[4] = clip8(q0 - delta);
-    put_line<VERT>(rw, seg, l, v);
+    const uint32_t P = rw[l][0], Q = rw[l][1];
+    const int delta = clip3(-tc, tc, lin(P, Q, W(0, 0, 1, -4), W(4, -1, 0, 0), 4) >> 3);
+    const int p0 = dp4(P, W(0, 0, 0, 1), 0), q0 = dp4(Q, W(1, 0, 0, 0), 0);
+    rw[l][0] = P + (uint32_t)(clip8(p0 + delta) - p0) * 16777216u;
+    rw[l][1] = Q + (uint32_t)(clip8(q0 - delta) - q0);
   }
   return true;
 }
@@ -217,8 +221,7 @@ __device__ __forceinline__ void deblock_cell(const Pic& pic, uint8_t* plane, int
   for (int g = 0; g < 4; g++) {
     if ((seg_do >> g) & 1u) {
       const int qp_sum = (int)((seg_qp >> (8 * g)) & 0xffu);
-      changed |= CIDX == 0 ? filter_luma_segment<true>(rw, 0, qp_sum, beta_off2, tc_off2)
-                           : filter_chroma_segment<true>(rw, 0, qp_sum, c_qp_off, tc_off2);
+      changed |= CIDX == 0 ? filter_luma_segment(rw, qp_sum, beta_off2, tc_off2) : filter_chroma_segment(rw, qp_sum, c_qp_off, tc_off2);
     }
 #pragma unroll
     for (int r = 0; r < 4; r++) {  // the other segment of this edge moves into rows 0..3 (and back after it)
