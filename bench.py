@@ -479,11 +479,15 @@ def main():
         dec.wait_job(j)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    # the plain synchronous call, one at a time, for comparison
+    # The plain synchronous call, one at a time: the other serving mode.  On one GPU it loses (nothing overlaps the copy); with
+    # all 8 ranks of a box copying at once it WINS, because the box's host memory system, not the GPUs, is the limit there
+    # (94-121 GB/s for eight concurrent device->host streams) and fewer concurrent DMA streams contend less.
+    barrier()
+    n_sync = 2 if world == 1 else 6
     t0 = time.perf_counter()
-    for _ in range(2):
+    for _ in range(n_sync):
         dec.decode_grids(images[:eb], out=out_np)
-    sync_s = (time.perf_counter() - t0) / 2
+    sync_s = (time.perf_counter() - t0) / n_sync
     e2e_val = eb * MP_PER_IMAGE / e2e_s
 
     # ---- aggregate over ranks: max time --------------------------------------------------------------------
@@ -493,8 +497,20 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
         e2e_val = eb * MP_PER_IMAGE / e2e_s
+        t = torch.tensor([sync_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sync_s = float(t[0])
     value = world * args.steps * n_img * MP_PER_IMAGE / (ms * 1e-3)
-    e2e_total = world * e2e_val
+    # e2e = the better of the two serving modes measured in this run (both through the C-ABI call with host buffers, both
+    # max over ranks); the line says which, and carries both figures
+    pipelined_total = world * e2e_val
+    sync_total = world * eb * MP_PER_IMAGE / sync_s
+    e2e_mode = "3 calls in flight: heic_b200_decode_grids_submit/_job_wait, pinned host RGB"
+    e2e_total = pipelined_total
+    if sync_total > pipelined_total:
+        e2e_total = sync_total
+        e2e_s = sync_s
+        e2e_mode = "one synchronous heic_b200_decode_grids call at a time per rank, pinned host RGB (faster than 3 calls in flight on this box)"
 
     # ---- the same colour stage with the irot rotation applied (apply_transforms = 1; every iPhone portrait has one) ------------
     rotated = None
@@ -612,8 +628,8 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": round(e2e_total, 2), "unit": "MP/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "images_per_call": eb, "host_affinity": affinity, "ms_per_call": round(e2e_s * 1e3, 3), "host_submit_ms_per_call": round(submit_s / e2e_steps * 1e3, 3),
-                    "mode": f"{N_BUF} calls in flight: heic_b200_decode_grids_submit/_job_wait, pinned host RGB",
-                    "synchronous_call_MPps": round(world * eb * MP_PER_IMAGE / sync_s, 2)},
+                    "mode": e2e_mode, "pipelined_3_in_flight_MPps": round(pipelined_total, 2),
+                    "synchronous_call_MPps": round(sync_total, 2)},
             "rotated_color": rotated,
             "copies_per_warp_upper_bound": converged,
             "gpu_launches": int(launches),
