@@ -683,7 +683,6 @@ struct Parser {
   };
   HEIC_HD void rc_begin(Rc& r, int log2, int c_idx, int pred_mode, int16_t* out) {
     const PicParams* pp = PP();
-    const int n = 1 << log2;
     int tskip = 0;
     if (pp->tskip_enabled && log2 <= 2) tskip = dec(CTX_TSKIP + (c_idx ? 1 : 0));
     int last_x, last_y;
@@ -716,8 +715,6 @@ HEIC_NO_UNROLL
     const int lg_sb = log2 - 2;
     const int last_sub_block = scan_inv(scan_idx, lg_sb, last_x >> 2, last_y >> 2);
     const int last_scan_pos = scan_inv(scan_idx, 2, last_x & 3, last_y & 3);
-    const int sb_w = 1 << lg_sb;
-    const int sig_base = CTX_SIG + (c_idx ? 27 : 0);
     // sigCtx offset for the non-4x4, non-DC case (9.3.4.2.5)
     const int sig_off = c_idx == 0 ? ((log2 == 3) ? (scan_idx == 0 ? 9 : 15) : 21) : ((log2 == 3) ? 9 : 12);
     r.k = (uint32_t)log2 | ((uint32_t)c_idx << 3) | ((uint32_t)scan_idx << 5) | ((uint32_t)sig_off << 7) |

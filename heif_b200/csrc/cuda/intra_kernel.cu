@@ -32,10 +32,6 @@ __device__ __forceinline__ uint32_t compact1(uint32_t v) {
 }
 __device__ __forceinline__ int clip8(int v) { return min(255, max(0, v)); }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
 __device__ __forceinline__ void cp_async16s(uint32_t smem_addr, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_addr), "l"(gmem_src) : "memory");
 }
