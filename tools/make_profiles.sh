@@ -13,11 +13,11 @@ for k in cabac_kernel intra_kernel transform_mma_kernel deblock_kernel; do
 done
 {
   echo "# cuobjdump -sass heif_b200/libheic_b200.so: instruction classes that show the Blackwell-specific paths (count of SASS lines)"
-  for pat in 'IMMA\.16832' 'IMMA\.16816' 'LDSM' 'UBLKCP' 'VIADDMNMX' 'LDGSTS' 'I2IP' 'REDUX'; do
+  for pat in 'IMMA\.16832' 'IMMA\.16816' 'LDSM' 'IDP\.4A' 'UBLKCP' 'VIADDMNMX' 'LDGSTS' 'I2IP' 'REDUX'; do
     printf "%-14s %s\n" "$pat" "$(cuobjdump -sass heif_b200/libheic_b200.so 2>/dev/null | grep -cE "$pat")"
   done
   echo; echo "# examples"
-  cuobjdump -sass heif_b200/libheic_b200.so 2>/dev/null | grep -E 'IMMA|LDSM|UBLKCP|VIADDMNMX|I2IP' | sed 's/ *\/\* 0x[0-9a-f]* \*\///' | awk '{$1=""; print}' | sort | uniq -c | sort -rn | head -24
+  cuobjdump -sass heif_b200/libheic_b200.so 2>/dev/null | grep -E 'IMMA|LDSM|IDP|UBLKCP|VIADDMNMX|I2IP' | sed 's/ *\/\* 0x[0-9a-f]* \*\///' | awk '{$1=""; print}' | sort | uniq -c | sort -rn | head -24
 } > $P/r02_sass_evidence.txt
 
 # ncu returns no DRAM counters for two kernels in the whole-decode capture (tu_list_kernel, deblock_kernel<0>): their bytes
