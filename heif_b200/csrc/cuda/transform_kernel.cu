@@ -119,7 +119,10 @@ __device__ __forceinline__ uint32_t classify(uint32_t w, bool chroma) {
   return cy | (cb << 3) | (cr << 6);
 }
 
-__global__ void __launch_bounds__(kListThreads) tu_list_kernel(Arenas A, uint32_t blocks_per_tile) {
+#ifndef HEIC_LIST_MIN_CTAS
+#define HEIC_LIST_MIN_CTAS 1
+#endif
+__global__ void __launch_bounds__(kListThreads, HEIC_LIST_MIN_CTAS) tu_list_kernel(Arenas A, uint32_t blocks_per_tile) {
   __shared__ uint32_t cta_cnt[LIST_CLASSES], cta_base[LIST_CLASSES], warp_base[kListThreads / 32][LIST_CLASSES];
   const uint32_t tile = blockIdx.x / blocks_per_tile;
   const uint32_t first = (blockIdx.x % blocks_per_tile) * kListPerCta;
