@@ -333,10 +333,12 @@ struct IntraLayout {
   int warp_bytes;
 };
 
-#ifndef HEIC_INTRA_MIN_CTAS
-#define HEIC_INTRA_MIN_CTAS 3
+// 72 registers: 28 one-warp CTAs per SM instead of 24 at 80, no spills (52.7 -> 50.7 ms per 592 images; 64 registers /
+// 32 warps measured slower, 53.6 ms, and so did 96 registers / 21 warps, 54.9 ms)
+#ifndef HEIC_INTRA_MAXNREG
+#define HEIC_INTRA_MAXNREG 72
 #endif
-__global__ void __launch_bounds__(256, HEIC_INTRA_MIN_CTAS) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, IntraLayout L, int clear_coeff) {
+__global__ void __maxnreg__(HEIC_INTRA_MAXNREG) intra_kernel(Arenas A, const uint32_t* __restrict__ order, int n_slots, IntraLayout L, int clear_coeff) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t tile = order[blockIdx.x];
   const TileParams* tp = A.tiles + tile;
