@@ -51,7 +51,7 @@ struct SP {
 };
 struct Ctu {
   int w, h, ctb, ctb4, x_ctb, y_ctb;
-  SP<uint8_t> buf[3];   // sample (x, y) relative to the CTU origin at buf[(y + 1) * stride + x + 16], x, y >= -1
+  SP<uint8_t> buf[3];   // sample (x, y) relative to the CTU origin at buf[(y + 1) * stride + x + kApron], x, y >= -1
   int stride[3];
   SP<uint8_t> ref;      // reference samples after substitution, s = 0 .. 4n (bottom-left -> corner -> top-right);
                         // the second block of a chroma pair (or the smoothed luma samples) at ref + kRefSpan
@@ -62,6 +62,7 @@ struct Ctu {
   int strong_flag;
 };
 constexpr int kRefSpan = 144, kRefaSpan = 104;
+constexpr int kApron = 4;  // bytes in front of a CTU buffer row: sample x = -1 is its last one
 
 __device__ __forceinline__ uint32_t pack4(int a, int b, int c, int d) {
   return (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)c << 16) | ((uint32_t)d << 24);
@@ -110,7 +111,7 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
     // left(i) is lane 8 - i and top(i) lane 8 + i), the 16 samples in lanes 0..15, and shuffles replace the reference
     // arrays, their loops and two warp barriers.  No smoothing at this size.  A chroma pair runs the same shuffles on a
     // second register (same mode, same geometry); the edge filters of DC / horizontal / vertical are luma only.
-    const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
+    const uint8_t* corner = buf + by * stride + bx + kApron - 1;  // sample (-1, -1)
     int r = 128, r2 = 128;
     if (lane <= 16 && lo <= hi) {
       const int d = min(max(lane, lo), hi) - 8;
@@ -166,7 +167,7 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
       }
     }
     if (lane < 16) {
-      uint8_t* o = buf + (by + 1 + y) * stride + bx + 16 + x;
+      uint8_t* o = buf + (by + 1 + y) * stride + bx + kApron + x;
       if (cbf_a) v = clip8(v + (int)resid[lane]);
       o[0] = (uint8_t)v;
       if (pair) {
@@ -178,7 +179,7 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
     return;
   }
   {
-    const uint8_t* corner = buf + by * stride + bx + 15;  // sample (-1, -1)
+    const uint8_t* corner = buf + by * stride + bx + kApron - 1;  // sample (-1, -1)
     const int n_ref = pair ? 2 * cnt : cnt;
     const int lo_d = lo - 2 * N, hi_d = hi - 2 * N;  // d <= 0: left column (upwards to the corner), d > 0: top row
     if (lo > hi) {
@@ -227,7 +228,7 @@ __device__ __forceinline__ void predict_block(const Ctu& c, bool pair, uint8_t* 
   const int n_items = pair ? 2 * quads : quads;
   const int lq = log2 - 2;                       // log2 of the quads per row
   const bool edge = !pair && N < 32;
-  uint8_t* out = buf + (by + 1) * stride + bx + 16;
+  uint8_t* out = buf + (by + 1) * stride + bx + kApron;
   // mode-specific setup
   int dc_pack = 0;
   const int angle = kIntraPredAngle[mode];
@@ -430,7 +431,7 @@ __global__ void __maxnreg__(HEIC_INTRA_MAXNREG) intra_kernel(Arenas A, const uin
         const int sub = pl ? 1 : 0, cs = c.ctb >> sub, st = c.stride[pl];
         uint8_t* b = c.buf[pl];
         if (rx > 0)
-          for (int y = lane; y < cs; y += 32) b[(y + 1) * st + 15] = b[(y + 1) * st + 16 + cs - 1];
+          for (int y = lane; y < cs; y += 32) b[(y + 1) * st + kApron - 1] = b[(y + 1) * st + kApron + cs - 1];
         if (ry > 0) {
           const int wp = c.w >> sub, x0 = (c.x_ctb >> sub) - 1, y0 = (c.y_ctb >> sub) - 1;
           // aligned 4-byte words from x_ctb - 4 (its last byte is the corner sample) to the end of the above-right CTU;
@@ -438,7 +439,7 @@ __global__ void __maxnreg__(HEIC_INTRA_MAXNREG) intra_kernel(Arenas A, const uin
           const uint8_t* src = plane[pl] + (size_t)y0 * pitch[pl];
           for (int j = lane; j <= cs / 2; j += 32) {
             const int x = x0 - 3 + 4 * j;
-            if (x >= 0 && x < wp) *reinterpret_cast<uint32_t*>(b + 12 + 4 * j) = __ldcg(reinterpret_cast<const uint32_t*>(src + x));
+            if (x >= 0 && x < wp) *reinterpret_cast<uint32_t*>(b + kApron - 4 + 4 * j) = __ldcg(reinterpret_cast<const uint32_t*>(src + x));
           }
         }
       }
@@ -519,7 +520,7 @@ __global__ void __maxnreg__(HEIC_INTRA_MAXNREG) intra_kernel(Arenas A, const uin
           const int y = i >> lw, xw = (i & ((1 << lw) - 1)) << 2;
           if (xw < wv)
             *reinterpret_cast<uint32_t*>(plane[pl] + (size_t)(yo + y) * pitch[pl] + xo + xw) =
-                *reinterpret_cast<const uint32_t*>(b + (y + 1) * st + 16 + xw);
+                *reinterpret_cast<const uint32_t*>(b + (y + 1) * st + kApron + xw);
         }
       }
       if (n_slots > 1) {
@@ -547,8 +548,11 @@ IntraLayout intra_layout(int log2_ctb) {
   o += 2 * kRefSpan;
   L.refa = o;
   o += 2 * kRefaSpan;
-  L.stride_y = 2 * ctb + 20;  // 16 bytes of apron on the left (alignment), the above-right CTU and slack on the right
-  L.stride_c = ctb + 20;
+  // a 4-byte apron on the left (the corner / left-column samples; 4-byte aligned word stores), the CTU and the above-right
+  // CTU: 17 and 9 words per row for 32x32 CTBs -- odd, so a column walks all banks -- and 7.3 KB per warp, so that 28 one-warp
+  // CTAs fit an SM (24 with the 16-byte apron and 4 bytes of slack this layout had before)
+  L.stride_y = 2 * ctb + kApron;
+  L.stride_c = ctb + kApron;
   L.buf0 = o;
   o += (ctb + 1) * L.stride_y;
   L.buf1 = o;
